@@ -1,0 +1,172 @@
+/* splashy_cuda.h -- C ABI of libsplashy_cuda.so
+ *
+ * B200 (sm_100a) implementation of the per-timestep hot path of
+ * cantsin/splashy: Convection.apply -> Pressure.calculate -> Pressure.apply
+ * (Simulator.fs:82,88-89), plus the validators of Simulator.fs:91-97.
+ *
+ * The reference has no FFI of its own; these entry points are
+ * what its F# host binds with [<DllImport("splashy_cuda")>] in place of the
+ * bodies of the functions cited on each declaration (see INTEGRATION.md for
+ * the P/Invoke shim).  Plain C: opaque context, plain pointers and sizes, no
+ * CUDA / torch types.  There is no CPU fallback: every entry point needs a
+ * CUDA device and fails with SPL_E_CUDA otherwise.
+ *
+ * Layout contract:
+ *   - dense box nx * ny * nz, x fastest:  idx = (k * ny + j) * nx + i
+ *   - u[idx] = x-velocity on the +x face of cell (i,j,k) (between i and i+1),
+ *     v, w likewise (Pressure.fs:18-31)
+ *   - media: 0 Air, 1 Fluid, 2 Solid (Cell.fs:9), 255 = cell absent from the
+ *     sparse grid; absent / out-of-box behaves like Solid and is never counted
+ *     as a neighbour (Pressure.fs:34-38)
+ *   - pressure p is defined on Fluid cells; Air is 0 (Constants.fs:20)
+ *   - dtype selects fp32 or fp64 for every field pointer of a context
+ *
+ * A context is not thread-safe; calls are synchronous (they return after the
+ * work is complete), like the reference's single-threaded blocking model.
+ */
+#ifndef SPLASHY_CUDA_H
+#define SPLASHY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPL_ABI_VERSION 1
+
+/* ---- enums ------------------------------------------------------------ */
+enum { SPL_F32 = 0, SPL_F64 = 1 };                          /* spl_desc.dtype  */
+enum { SPL_PC_NONE = 0, SPL_PC_JACOBI = 1, SPL_PC_RBIC0 = 2 }; /* .precond     */
+enum { SPL_AIR = 0, SPL_FLUID = 1, SPL_SOLID = 2, SPL_ABSENT = 255 };
+
+/* quirk mask: reproduce the reference's literal Convection.fs behaviour
+ * (SURVEY.md Q3-Q5).  0 = intended semi-Lagrangian semantics.              */
+enum {
+  SPL_Q_REF_INTERP    = 1u << 0, /* Convection.fs:35,42-47 offsets + int-snap key */
+  SPL_Q_FORWARD_TRACE = 1u << 1, /* Convection.fs:54,56 sign                       */
+  SPL_Q_NEAREST_COPY  = 1u << 2  /* Convection.fs:57,63-64 whole-vector copy       */
+};
+
+/* return codes; text from spl_last_error mirrors the reference's failwith   */
+enum {
+  SPL_OK              =  0,
+  SPL_E_BADARG        = -1,
+  SPL_E_CUDA          = -2,  /* CUDA / NCCL runtime error, or no device             */
+  SPL_E_TRACE         = -3,  /* Convection.fs:65 "Backwards particle trace went too far." */
+  SPL_E_NONFINITE     = -4,  /* Vector.fs:17 / Pressure.fs:138-142                  */
+  SPL_E_DIVERGENCE    = -5,  /* Pressure.fs:149 "Velocity field is not correct"     */
+  SPL_E_NOT_CONVERGED = -6,  /* PCG hit max_iters (no reference counterpart)        */
+  SPL_E_STATE         = -7   /* call order (e.g. project before upload)             */
+};
+
+/* ---- descriptor (replaces the [<Literal>]s of Constants.fs:10-36) -------- */
+typedef struct spl_desc {
+  int      nx, ny, nz;     /* this context's box (one z-slab when world > 1)  */
+  double   h;              /* Constants.fs:11  cell size                      */
+  double   rho;            /* Constants.fs:15  fluid_density                  */
+  int      dtype;          /* SPL_F32 | SPL_F64                               */
+  int      precond;        /* SPL_PC_*                                        */
+  double   tol;            /* stop when max|r| <= tol * max|b|; 0 = never     */
+  int      max_iters;      /* PCG iteration cap                               */
+  double   tau;            /* SPL_PC_RBIC0: relaxed-MIC weight in [0,1)       */
+  unsigned quirks;         /* SPL_Q_* mask                                    */
+  int      origin[3];      /* world cell index of box cell (0,0,0); used by
+                              SPL_Q_REF_INTERP only (Coord.fs:49-61)          */
+  int      device;         /* CUDA device ordinal                             */
+  /* z-slab decomposition, one process per GPU (world = 1: single GPU)       */
+  int      rank, world;
+  int      nz_global;      /* total planes over all slabs (0 => nz)           */
+  int      z0;             /* global index of this slab's first plane         */
+  const void* nccl_id;     /* world > 1: 128-byte ncclUniqueId from
+                              spl_nccl_unique_id, identical on every rank     */
+  double   gravity[3];     /* Constants.fs:26, used by spl_add_forces         */
+} spl_desc;
+
+/* result block (SURVEY.md section 5 "metrics")                              */
+typedef struct spl_info {
+  int      iters;          /* PCG iterations run                              */
+  int      converged;      /* 1 if the stopping test was met                  */
+  double   r_inf;          /* max |r| at exit                                 */
+  double   b_inf;          /* max |b|                                         */
+  double   max_abs_div;    /* max |in - out| over Fluid after projection      */
+  int64_t  nonfinite;      /* non-finite u,v,w,p entries                      */
+  int64_t  trace_escapes;  /* departure points that left the halo / box       */
+  float    ms_advect, ms_rhs, ms_solve, ms_grad, ms_total; /* CUDA events     */
+  int64_t  kernel_launches;/* kernels launched by the last call               */
+} spl_info;
+
+typedef struct spl_ctx spl_ctx;
+
+/* ---- lifetime ----------------------------------------------------------- */
+void spl_desc_default(spl_desc* d);  /* Constants.fs values, fp32, Jacobi     */
+int  spl_create(spl_ctx** out, const spl_desc* desc);
+void spl_destroy(spl_ctx* ctx);
+/* message of the last failure on ctx (or of the last failed spl_create when
+ * ctx == NULL); the text mirrors the reference's failwith strings
+ * (Convection.fs:65, Pressure.fs:138-149, Vector.fs:17).                    */
+const char* spl_last_error(const spl_ctx* ctx);
+int  spl_abi_version(void);
+int  spl_device_count(void);
+/* fills 128 bytes; rank 0 calls it and hands the bytes to every rank         */
+int  spl_nccl_unique_id(void* out128);
+
+/* ---- state: replaces Grid.fs:12 (the global Dictionary<Coord,Cell>) ------- */
+/* host -> device.  media is required; u, v, w, p may be NULL (= zeros).
+ * Replaces Grid.add_cells / update_velocities / update_pressures
+ * (Grid.fs:38,49-59) as the way state enters the solver.                    */
+int  spl_upload(spl_ctx* ctx, const uint8_t* media, const void* u,
+                const void* v, const void* w, const void* p);
+/* device -> host; every pointer may be NULL.  div = (incoming - outgoing) of
+ * Pressure.fs:16-32 for the current velocities (0 on non-Fluid cells).      */
+int  spl_download(spl_ctx* ctx, void* u, void* v, void* w, void* p, void* div);
+
+/* ---- the hot path -------------------------------------------------------- */
+/* Convection.apply + Grid.update_velocities (Convection.fs:60-66,
+ * Simulator.fs:82)                                                           */
+int  spl_advect(spl_ctx* ctx, double dt, spl_info* info);
+/* Forces.apply (Forces.fs:6-12, Simulator.fs:84): v += gravity * dt on Fluid */
+int  spl_add_forces(spl_ctx* ctx, double dt);
+/* Pressure.divergence over every Fluid cell (Pressure.fs:16-32) -> kept on the
+ * device as the PCG right-hand side b = (h rho/dt) * div (Pressure.fs:64-68) */
+int  spl_divergence(spl_ctx* ctx, double dt, spl_info* info);
+/* Pressure.calculate + Grid.update_pressures + Pressure.apply +
+ * Grid.update_velocities (Pressure.fs:41-72,115-129; Simulator.fs:88-89)     */
+int  spl_project(spl_ctx* ctx, double dt, spl_info* info);
+/* Pressure.check_pressures + check_divergence (Pressure.fs:132-149);
+ * returns SPL_E_NONFINITE / SPL_E_DIVERGENCE like the reference throws.      */
+int  spl_check(spl_ctx* ctx, double div_tol, spl_info* info);
+/* advect -> rhs -> PCG -> gradient in one call (Simulator.fs:82,88-89)        */
+int  spl_step(spl_ctx* ctx, double dt, spl_info* info);
+
+/* ---- benchmarking helpers ------------------------------------------------ */
+/* page-locked host buffers for the upload / download calls                   */
+void* spl_host_alloc(size_t bytes);
+void  spl_host_free(void* p);
+/* keep a copy of the current u,v,w on the device / restore it (lets a bench
+ * repeat the same step without a host round trip)                            */
+int  spl_snapshot(spl_ctx* ctx);
+int  spl_restore(spl_ctx* ctx);
+/* run exactly `iters` PCG iterations in spl_project / spl_step regardless of
+ * tol (0 restores the tolerance-driven loop)                                 */
+int  spl_set_fixed_iters(spl_ctx* ctx, int iters);
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel of
+ * this library is launched on): start records an event, stop records a second
+ * one, waits for it and returns the elapsed device time in milliseconds.      */
+int  spl_timer_start(spl_ctx* ctx);
+int  spl_timer_stop(spl_ctx* ctx, float* ms);
+/* per-kernel timing of the PCG iteration: builds the RHS for dt, then runs
+ * `iters` (<= 256) iterations with CUDA events around every phase-A and
+ * phase-B launch; returns the average duration of each in milliseconds.  The
+ * velocity field is not modified (no gradient subtraction).                   */
+int  spl_profile_pcg(spl_ctx* ctx, double dt, int iters, float* ms_phase_a,
+                     float* ms_phase_b);
+/* device pointer of a field including its z-halo (plumbing for tests):
+ * which = 0 u,1 v,2 w,3 p,4 r,5 media,6 codes ; *halo_planes receives hz      */
+void* spl_device_ptr(spl_ctx* ctx, int which, int* halo_planes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLASHY_CUDA_H */

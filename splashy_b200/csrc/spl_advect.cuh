@@ -1,0 +1,265 @@
+// spl_advect.cuh -- semi-Lagrangian advection of the staggered MAC velocity
+// (sm_100a).  Replaces Convection.apply + Grid.update_velocities
+// (Convection.fs:50-66, Simulator.fs:82).
+//
+// Intended semantics: for every Fluid cell and each of its three
+// +faces, RK2-midpoint backtrace from the face centre through the staggered
+// velocity field, then trilinear sample of that component at the departure
+// point.  Corners outside the box contribute 0 (Convection.fs:36-38 "None ->
+// 0").  Jacobi update: reads (u,v,w), writes (u2,v2,w2).
+//
+// Positions are kept as (integer cell, small real offset) so fp32 does not
+// lose the fractional part on 512^3 / 4096^2 grids.
+#pragma once
+#include "spl_common.cuh"
+
+namespace spl {
+
+template <typename T>
+struct FieldView {
+  const T* __restrict__ f;
+  int nx, ny;
+  int klo, khi;       // local planes that exist in the global box  [klo, khi)
+  int hlo, hhi;       // local planes that exist in memory          [hlo, hhi)
+  long long plane;
+};
+
+template <typename T>
+__device__ __forceinline__ T fetch(const FieldView<T>& F, int i, int j, int k,
+                                   unsigned& escaped) {
+  if ((unsigned)i >= (unsigned)F.nx || (unsigned)j >= (unsigned)F.ny) return T(0);
+  if (k < F.klo || k >= F.khi) return T(0);
+  if (k < F.hlo || k >= F.hhi) { escaped = 1u; return T(0); }
+  return F.f[(long long)k * F.plane + (long long)j * F.nx + i];
+}
+
+// Convection.fs:21-39 with the intended corner key: weights [1-f, f] per axis,
+// sum nested x', y', z'.  Sample point = (bi + ox, bj + oy, bk + oz).
+template <typename T>
+__device__ __forceinline__ T sample(const FieldView<T>& F, int bi, int bj, int bk,
+                                    T ox, T oy, T oz, unsigned& escaped) {
+  const T fx = floor(ox), fy = floor(oy), fz = floor(oz);
+  const T wx1 = ox - fx, wy1 = oy - fy, wz1 = oz - fz;
+  const T wx[2] = {T(1) - wx1, wx1};
+  const T wy[2] = {T(1) - wy1, wy1};
+  const T wz[2] = {T(1) - wz1, wz1};
+  const int i0 = bi + (int)fx, j0 = bj + (int)fy, k0 = bk + (int)fz;
+  T total = T(0);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        total += fetch(F, i0 + a, j0 + b, k0 + c, escaped) * wx[a] * wy[b] * wz[c];
+  return total;
+}
+
+// new value of component `comp` on the +face of cell (i,j,k)
+template <typename T>
+__device__ __forceinline__ T advect_face(const FieldView<T>& U, const FieldView<T>& V,
+                                         const FieldView<T>& W, int comp, int i, int j,
+                                         int k, T c /* sgn*dt/h */, unsigned& esc) {
+  const T h = T(0.5);
+  // offset of the face centre from the sample lattice of each component:
+  // sampling component b at (face of a) + d uses offset d + e_a/2 - e_b/2
+  const T ax = (comp == 0) ? h : T(0), ay = (comp == 1) ? h : T(0),
+          az = (comp == 2) ? h : T(0);
+  // stage 0: velocity at the face centre
+  const T u0 = sample(U, i, j, k, ax - h, ay, az, esc);
+  const T v0 = sample(V, i, j, k, ax, ay - h, az, esc);
+  const T w0 = sample(W, i, j, k, ax, ay, az - h, esc);
+  // midpoint
+  const T mx = h * c * u0, my = h * c * v0, mz = h * c * w0;
+  const T u1 = sample(U, i, j, k, mx + ax - h, my + ay, mz + az, esc);
+  const T v1 = sample(V, i, j, k, mx + ax, my + ay - h, mz + az, esc);
+  const T w1 = sample(W, i, j, k, mx + ax, my + ay, mz + az - h, esc);
+  // departure point, sampled on this component's own lattice
+  const T dx = c * u1, dy = c * v1, dz = c * w1;
+  const FieldView<T>& F = (comp == 0) ? U : (comp == 1) ? V : W;
+  return sample(F, i, j, k, dx, dy, dz, esc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_advect(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ u,
+         const T* __restrict__ v, const T* __restrict__ w, T* __restrict__ u2,
+         T* __restrict__ v2, T* __restrict__ w2, T c, Scal* __restrict__ sc) {
+  FieldView<T> U{u, g.nx, g.ny, -g.z0, g.nzg - g.z0, -g.hz, g.nz + g.hz, g.plane};
+  FieldView<T> V = U, W = U;
+  V.f = v;
+  W.f = w;
+  unsigned esc = 0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    T nu = u[idx], nv = v[idx], nw = w[idx];
+    if (media[idx] == FLUID) {
+      const int i = (int)(idx % g.nx);
+      const long long t = idx / g.nx;
+      const int j = (int)(t % g.ny);
+      const int k = (int)(t / g.ny);
+      nu = advect_face<T>(U, V, W, 0, i, j, k, c, esc);
+      nv = advect_face<T>(U, V, W, 1, i, j, k, c, esc);
+      nw = advect_face<T>(U, V, W, 2, i, j, k, c, esc);
+    }
+    u2[idx] = nu;
+    v2[idx] = nv;
+    w2[idx] = nw;
+  }
+  if (esc) atomicAdd(&sc->escapes, 1ull);
+}
+
+// ---- literal reference behaviour (quirk flags) ----------------------
+// Coord.fs:49-57 with .NET remainder semantics
+__device__ __forceinline__ int ref_nearest(int n) {
+  const int h = 10;
+  const int r = n % h;          // C++ % truncates like .NET
+  if (r == 0) return n;
+  if (r >= h / 2) return n + (h - r);
+  return n - r;
+}
+
+struct QuirkCfg {
+  unsigned quirks;
+  int ox, oy, oz;     // world cell index of local cell (0,0,0) (oz includes z0)
+  double h;
+};
+
+// One thread per Fluid cell, fp64 arithmetic regardless of the storage type.
+// With all three flags set this is Convection.fs:21-66 verbatim except for the
+// commit order (Jacobi instead of the reference's in-place Seq.iter).
+template <typename T>
+__device__ __forceinline__ double q_fetch(const QuirkCfg& q, const FieldView<T>& F,
+                                          int wi, int wj, int wk, bool& present,
+                                          const uint8_t* __restrict__ media,
+                                          unsigned& esc) {
+  // world cell index -> box index
+  const int i = wi - q.ox, j = wj - q.oy, k = wk - q.oz;
+  present = false;
+  if ((unsigned)i >= (unsigned)F.nx || (unsigned)j >= (unsigned)F.ny) return 0.0;
+  if (k < F.klo || k >= F.khi) return 0.0;
+  if (k < F.hlo || k >= F.hhi) { esc = 1u; return 0.0; }
+  const long long idx = (long long)k * F.plane + (long long)j * F.nx + i;
+  if (media[idx] == ABSENT) return 0.0;
+  present = true;
+  return (double)F.f[idx];
+}
+
+template <typename T>
+__device__ __forceinline__ double q_interp(const QuirkCfg& q, const FieldView<T>& F,
+                                           const uint8_t* __restrict__ media, double x,
+                                           double y, double z, unsigned& esc) {
+  // Convection.fs:21-39; x, y, z in index units (metres / h)
+  const double i = floor(x), j = floor(y), k = floor(z);
+  const int ii = (int)i, jj = (int)j, kk = (int)k;
+  const double id[2] = {i - x + 1.0, x - i};
+  const double jd[2] = {j - y + 1.0, y - j};
+  const double kd[2] = {k - z + 1.0, z - k};
+  double total = 0.0;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      for (int c = 0; c < 2; ++c) {
+        int wi, wj, wk;
+        if (q.quirks & 1u) {
+          // Q3: int overload of Coord.construct applied to *index* values, the
+          // result read as metres: world cell index = nearest(n) / 10
+          wi = ref_nearest(ii + a) / 10;
+          wj = ref_nearest(jj + b) / 10;
+          wk = ref_nearest(kk + c) / 10;
+        } else {
+          wi = ii + a; wj = jj + b; wk = kk + c;
+        }
+        bool present;
+        const double val = q_fetch(q, F, wi, wj, wk, present, media, esc);
+        total += present ? val * id[a] * jd[b] * kd[c] : 0.0;
+      }
+  return total;
+}
+
+template <typename T>
+__device__ __forceinline__ void q_velocity(const QuirkCfg& q, const FieldView<T>& U,
+                                           const FieldView<T>& V, const FieldView<T>& W,
+                                           const uint8_t* __restrict__ media, double X,
+                                           double Y, double Z, double out[3],
+                                           unsigned& esc) {
+  // Convection.fs:41-48 (metres in)
+  const double xh = X / q.h, yh = Y / q.h, zh = Z / q.h;
+  if (q.quirks & 1u) {
+    out[0] = q_interp(q, U, media, xh, yh - 0.5, zh - 0.5, esc);
+    out[1] = q_interp(q, V, media, xh - 0.5, yh, zh - 0.5, esc);
+    out[2] = q_interp(q, W, media, xh - 0.5, yh - 0.5, zh, esc);
+  } else {
+    out[0] = q_interp(q, U, media, xh - 0.5, yh, zh, esc);
+    out[1] = q_interp(q, V, media, xh, yh - 0.5, zh, esc);
+    out[2] = q_interp(q, W, media, xh, yh, zh - 0.5, esc);
+  }
+}
+
+__device__ __forceinline__ int ref_round_nearest(double x) {
+  // Coord.fs:65-67: round (banker's) -> int -> nearest
+  return ref_nearest((int)rint(x));
+}
+
+template <typename T>
+__global__ void k_advect_quirk(Geo g, QuirkCfg q, const uint8_t* __restrict__ media,
+                               const T* __restrict__ u, const T* __restrict__ v,
+                               const T* __restrict__ w, T* __restrict__ u2,
+                               T* __restrict__ v2, T* __restrict__ w2, double dt,
+                               Scal* __restrict__ sc, int* __restrict__ too_far) {
+  FieldView<T> U{u, g.nx, g.ny, -g.z0, g.nzg - g.z0, -g.hz, g.nz + g.hz, g.plane};
+  FieldView<T> V = U, W = U;
+  V.f = v;
+  W.f = w;
+  unsigned esc = 0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    T nu = u[idx], nv = v[idx], nw = w[idx];
+    if (media[idx] == FLUID) {
+      const int i = (int)(idx % g.nx);
+      const long long t = idx / g.nx;
+      const int j = (int)(t % g.ny);
+      const int k = (int)(t / g.ny);
+      const double sgn = (q.quirks & 2u) ? 1.0 : -1.0;       // Q4
+      const double cx = (i + q.ox) * q.h, cy = (j + q.oy) * q.h,
+                   cz = (k + q.oz) * q.h;
+      if (q.quirks & 4u) {
+        // Q5: one trace from the cell coordinate, whole-vector nearest copy
+        double v0[3], v1[3];
+        q_velocity(q, U, V, W, media, cx, cy, cz, v0, esc);
+        q_velocity(q, U, V, W, media, cx + sgn * v0[0] * (dt / 2.0),
+                   cy + sgn * v0[1] * (dt / 2.0), cz + sgn * v0[2] * (dt / 2.0), v1, esc);
+        const int px = ref_round_nearest(cx + sgn * v1[0] * dt) / 10;
+        const int py = ref_round_nearest(cy + sgn * v1[1] * dt) / 10;
+        const int pz = ref_round_nearest(cz + sgn * v1[2] * dt) / 10;
+        bool p0, p1, p2;
+        const double a = q_fetch(q, U, px, py, pz, p0, media, esc);
+        const double b = q_fetch(q, V, px, py, pz, p1, media, esc);
+        const double c = q_fetch(q, W, px, py, pz, p2, media, esc);
+        if (!p0) atomicExch(too_far, 1);   // Convection.fs:65
+        nu = (T)a; nv = (T)b; nw = (T)c;
+      } else {
+        // per-face trace with the selected sampler / sign
+        double res[3];
+        for (int comp = 0; comp < 3; ++comp) {
+          const double fx = cx + (comp == 0 ? 0.5 * q.h : 0.0);
+          const double fy = cy + (comp == 1 ? 0.5 * q.h : 0.0);
+          const double fz = cz + (comp == 2 ? 0.5 * q.h : 0.0);
+          double v0[3], v1[3], v2d[3];
+          q_velocity(q, U, V, W, media, fx, fy, fz, v0, esc);
+          q_velocity(q, U, V, W, media, fx + sgn * v0[0] * (dt / 2.0),
+                     fy + sgn * v0[1] * (dt / 2.0), fz + sgn * v0[2] * (dt / 2.0), v1, esc);
+          q_velocity(q, U, V, W, media, fx + sgn * v1[0] * dt, fy + sgn * v1[1] * dt,
+                     fz + sgn * v1[2] * dt, v2d, esc);
+          res[comp] = v2d[comp];
+        }
+        nu = (T)res[0]; nv = (T)res[1]; nw = (T)res[2];
+      }
+    }
+    u2[idx] = nu;
+    v2[idx] = nv;
+    w2[idx] = nw;
+  }
+  if (esc) atomicAdd(&sc->escapes, 1ull);
+}
+
+}  // namespace spl

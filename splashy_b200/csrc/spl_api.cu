@@ -1,0 +1,916 @@
+// spl_api.cu -- C ABI of libsplashy_cuda.so (include/splashy_cuda.h)
+//
+// Host-side runtime of the advect -> project path: owns the device arrays that
+// replace the reference's global Dictionary<Coord,Cell> (Grid.fs:12), sequences
+// the kernels of spl_advect.cuh / spl_stencil.cuh / spl_pcg.cuh on one CUDA
+// stream, and -- when the box is one z-slab of a larger grid -- exchanges halo
+// planes and the CG scalars with the neighbouring ranks through NCCL (loaded
+// with dlopen so a single-GPU host needs no NCCL at all).
+//
+// There is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+
+#include "../../include/splashy_cuda.h"
+#include "spl_advect.cuh"
+#include "spl_common.cuh"
+#include "spl_pcg.cuh"
+#include "spl_stencil.cuh"
+
+using namespace spl;
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen
+// ---------------------------------------------------------------------------
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t,
+                       cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t,
+                       cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) {
+    err = std::string("cannot load libnccl: ") + dlerror();
+    return false;
+  }
+#define SPL_SYM(field, name)                                        \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name)); \
+  if (!g_nccl.field) { err = std::string("libnccl lacks ") + name; return false; }
+  SPL_SYM(GetUniqueId, "ncclGetUniqueId")
+  SPL_SYM(CommInitRank, "ncclCommInitRank")
+  SPL_SYM(CommDestroy, "ncclCommDestroy")
+  SPL_SYM(AllGather, "ncclAllGather")
+  SPL_SYM(Send, "ncclSend")
+  SPL_SYM(Recv, "ncclRecv")
+  SPL_SYM(GroupStart, "ncclGroupStart")
+  SPL_SYM(GroupEnd, "ncclGroupEnd")
+  SPL_SYM(GetErrorString, "ncclGetErrorString")
+#undef SPL_SYM
+  g_nccl.lib = lib;
+  return true;
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct spl_ctx {
+  spl_desc d{};
+  Geo g{};
+  size_t esz = 4;              // bytes per real
+  int vec = 1;                 // x cells per thread in the vector kernels
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6]{};
+  cudaEvent_t tev[2]{};        // spl_timer_*
+  cudaEvent_t* pev = nullptr;  // spl_profile_pcg: 3 events per iteration
+  int profile_iters = 0;       // > 0 while spl_profile_pcg runs
+  // fields, allocation start (plane -hz); *_0 = plane 0
+  void* alloc[16]{};
+  char *u = nullptr, *v = nullptr, *w = nullptr;     // current velocity (plane 0)
+  char *u2 = nullptr, *v2 = nullptr, *w2 = nullptr;  // advection target
+  char *su = nullptr, *sv = nullptr, *sw = nullptr;  // snapshot
+  char *p = nullptr, *r = nullptr, *sa = nullptr, *sb = nullptr, *q = nullptr;
+  char *z = nullptr, *einv = nullptr;
+  uint8_t *media = nullptr, *codes = nullptr;
+  Scal* sc = nullptr;          // device
+  Scal* hsc = nullptr;         // pinned mirror
+  double* partials = nullptr;  // 2 * MAX_PARTIALS
+  int* flag = nullptr;         // device int (quirk "too far")
+  int* hflag = nullptr;        // pinned
+  ncclComm_t comm = nullptr;
+  bool uploaded = false, have_rhs = false, have_snapshot = false;
+  int fixed_iters = 0;
+  int zchunk_override = 0;
+  int64_t launches = 0;
+  double rhs_dt = 0.0;
+  std::string err;
+};
+
+namespace {
+
+int fail(spl_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                               \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess)                                                     \
+      return fail(c, SPL_E_CUDA, "CUDA error %s at %s:%d (%s)",                \
+                  cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define NC(call)                                                               \
+  do {                                                                         \
+    ncclResult_t r_ = (call);                                                  \
+    if (r_ != ncclSuccess)                                                     \
+      return fail(c, SPL_E_CUDA, "NCCL error %d at %s:%d (%s)", (int)r_,       \
+                  __FILE__, __LINE__, g_nccl.GetErrorString(r_));              \
+  } while (0)
+
+#define LAUNCH(c, kernel, grid, block, ...)                                    \
+  do {                                                                         \
+    kernel<<<grid, block, 0, (c)->stream>>>(__VA_ARGS__);                      \
+    (c)->launches++;                                                           \
+  } while (0)
+
+inline int grid_for(const spl_ctx* c, long long n, int block = 256) {
+  long long need = (n + block - 1) / block;
+  long long cap = (long long)c->sms * 8;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+size_t field_bytes(const spl_ctx* c, size_t es) {
+  return (size_t)c->g.plane * (size_t)(c->g.nz + 2 * c->g.hz) * es;
+}
+
+int alloc_field(spl_ctx* c, int slot, size_t es, char** plane0, int fill) {
+  void* ptr = nullptr;
+  const size_t bytes = field_bytes(c, es);
+  CU(cudaMalloc(&ptr, bytes));
+  CU(cudaMemsetAsync(ptr, fill, bytes, c->stream));
+  c->alloc[slot] = ptr;
+  *plane0 = static_cast<char*>(ptr) + (size_t)c->g.hz * c->g.plane * es;
+  return SPL_OK;
+}
+
+ncclDataType_t nccl_real(const spl_ctx* c) {
+  return c->d.dtype == SPL_F64 ? ncclDouble : ncclFloat;
+}
+
+// exchange `width` z-planes of a field with both slab neighbours
+int exchange_halo(spl_ctx* c, char* plane0, size_t es, ncclDataType_t ty, int width) {
+  if (c->d.world <= 1) return SPL_OK;
+  const Geo& g = c->g;
+  if (width > g.hz) width = g.hz;
+  if (width > g.nz) width = g.nz;
+  const size_t cnt = (size_t)g.plane * width;
+  const size_t pb = (size_t)g.plane * es;
+  NC(g_nccl.GroupStart());
+  if (c->d.rank > 0) {
+    NC(g_nccl.Send(plane0, cnt, ty, c->d.rank - 1, c->comm, c->stream));
+    NC(g_nccl.Recv(plane0 - (size_t)width * pb, cnt, ty, c->d.rank - 1, c->comm, c->stream));
+  }
+  if (c->d.rank < c->d.world - 1) {
+    NC(g_nccl.Send(plane0 + (size_t)(g.nz - width) * pb, cnt, ty, c->d.rank + 1, c->comm,
+                   c->stream));
+    NC(g_nccl.Recv(plane0 + (size_t)g.nz * pb, cnt, ty, c->d.rank + 1, c->comm, c->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  return SPL_OK;
+}
+
+int exchange_velocity(spl_ctx* c, int width) {
+  int rc;
+  if ((rc = exchange_halo(c, c->u, c->esz, nccl_real(c), width))) return rc;
+  if ((rc = exchange_halo(c, c->v, c->esz, nccl_real(c), width))) return rc;
+  return exchange_halo(c, c->w, c->esz, nccl_real(c), width);
+}
+
+// complete the per-rank slots of the PCG scalars on every rank
+int gather_slots(spl_ctx* c, double* slots, int per_rank) {
+  if (c->d.world <= 1) return SPL_OK;
+  NC(g_nccl.AllGather(slots + (size_t)c->d.rank * per_rank, slots, per_rank, ncclDouble,
+                      c->comm, c->stream));
+  return SPL_OK;
+}
+
+int pull_scal(spl_ctx* c) {
+  CU(cudaMemcpyAsync(c->hsc, c->sc, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
+}
+
+__global__ void k_set_bmax(Scal* sc) { sc->bmax = rmax_of(sc, 0); }
+
+__global__ void k_finalize(Scal* sc, int par_last) {
+  if (sc->done) return;
+  const double rmax = rmax_of(sc, par_last);
+  sc->rmax = rmax;
+  sc->iters = sc->count;
+  const bool bad = !(rmax == rmax);
+  sc->breakdown = bad ? 1 : 0;
+  sc->converged = (!bad && rmax <= sc->tol * sc->bmax) ? 1 : 0;
+}
+
+int phaseA_zchunk(const spl_ctx* c, int tiles_xy) {
+  if (c->zchunk_override > 0) return c->zchunk_override;
+  const int nz = c->g.nz;
+  const int target_blocks = c->sms * 8 * 4;
+  int gz = (target_blocks + tiles_xy - 1) / tiles_xy;
+  if (gz < 1) gz = 1;
+  int zc = (nz + gz - 1) / gz;
+  if (zc < 8) zc = 8;
+  if (zc > nz) zc = nz;
+  while ((long long)tiles_xy * ((nz + zc - 1) / zc) > MAX_PARTIALS) zc *= 2;
+  return zc;
+}
+
+// ---- typed implementation -------------------------------------------------------
+template <typename T>
+struct Impl {
+  static T* P(char* p) { return reinterpret_cast<T*>(p); }
+
+  static int advect(spl_ctx* c, double dt) {
+    const Geo& g = c->g;
+    int rc = exchange_velocity(c, g.hz);
+    if (rc) return rc;
+    const int grid = grid_for(c, g.ncell);
+    if (c->d.quirks) {
+      QuirkCfg q{c->d.quirks, c->d.origin[0], c->d.origin[1], c->d.origin[2] + g.z0, c->d.h};
+      CU(cudaMemsetAsync(c->flag, 0, sizeof(int), c->stream));
+      LAUNCH(c, k_advect_quirk<T>, grid, 256, g, q, c->media, P(c->u), P(c->v), P(c->w),
+             P(c->u2), P(c->v2), P(c->w2), dt, c->sc, c->flag);
+    } else {
+      const T cc = T(-(dt / c->d.h));
+      LAUNCH(c, k_advect<T>, grid, 256, g, c->media, P(c->u), P(c->v), P(c->w), P(c->u2),
+             P(c->v2), P(c->w2), cc, c->sc);
+    }
+    CU(cudaGetLastError());
+    std::swap(c->u, c->u2);
+    std::swap(c->v, c->v2);
+    std::swap(c->w, c->w2);
+    return SPL_OK;
+  }
+
+  static int forces(spl_ctx* c, double dt) {
+    const Geo& g = c->g;
+    LAUNCH(c, k_forces<T>, grid_for(c, g.ncell), 256, g, c->media, P(c->u), P(c->v), P(c->w),
+           T(c->d.gravity[0] * dt), T(c->d.gravity[1] * dt), T(c->d.gravity[2] * dt));
+    CU(cudaGetLastError());
+    return SPL_OK;
+  }
+
+  static int rhs(spl_ctx* c, T scale, char* out) {
+    const Geo& g = c->g;
+    int rc = exchange_velocity(c, 1);
+    if (rc) return rc;
+    LAUNCH(c, k_div_rhs<T>, grid_for(c, g.ncell), 256, g, c->codes, P(c->u), P(c->v),
+           P(c->w), P(out), scale);
+    CU(cudaGetLastError());
+    return SPL_OK;
+  }
+
+  template <int VEC, int PC>
+  static int pcg(spl_ctx* c) {
+    const Geo& g = c->g;
+    const size_t fb = field_bytes(c, sizeof(T));
+    // x = 0, s = 0 (with halos), q = 0
+    CU(cudaMemsetAsync(c->alloc[6], 0, fb, c->stream));   // p
+    CU(cudaMemsetAsync(c->alloc[8], 0, fb, c->stream));   // sa
+    CU(cudaMemsetAsync(c->alloc[9], 0, fb, c->stream));   // sb
+    CU(cudaMemsetAsync(c->alloc[10], 0, fb, c->stream));  // q
+    // scalars
+    Scal* h = c->hsc;
+    const unsigned long long keep_nf = 0;
+    memset(h, 0, sizeof(Scal));
+    h->world = c->d.world;
+    h->rank = c->d.rank;
+    h->tol = c->fixed_iters > 0 ? 0.0 : c->d.tol;
+    h->nonfinite = keep_nf;
+    for (int w = 0; w < c->d.world; ++w)
+      h->gBM[1][w][0] = (w == 0) ? std::numeric_limits<double>::infinity() : 0.0;
+    CU(cudaMemcpyAsync(c->sc, h, sizeof(Scal), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // h is reused below
+
+    const int gridB = grid_for(c, g.ncell / VEC);
+    const int tx = (g.nx + 32 * VEC - 1) / (32 * VEC);
+    const int ty = (g.ny + TILE_Y - 1) / TILE_Y;
+    const int zc = phaseA_zchunk(c, tx * ty);
+    const dim3 gridA(tx, ty, (g.nz + zc - 1) / zc);
+    const dim3 blockA(32, TILE_Y);
+    const T* zr = (PC == PC_RBIC0) ? P(c->z) : P(c->r);
+
+    // rho_0 = r.z, max|b|  (phase B with alpha = 0)
+    LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->p), P(c->r), P(c->sa),
+           P(c->q), P(c->z), c->sc, c->partials, 0, 1);
+    int rc = gather_slots(c, &c->sc->gBM[0][0][0], 2);
+    if (rc) return rc;
+    LAUNCH(c, k_set_bmax, 1, 1, c->sc);
+    CU(cudaGetLastError());
+
+    const int limit = c->fixed_iters > 0 ? c->fixed_iters : c->d.max_iters;
+    char* sold = c->sa;
+    char* snew = c->sb;
+    int it = 0;
+    bool done = false;
+    const int poll = 16;
+    while (it < limit && !done) {
+      const int stop = (it + poll < limit) ? it + poll : limit;
+      for (; it < stop;) {
+        ++it;
+        const int par = it & 1;
+        if (c->d.world > 1) {
+          LAUNCH(c, (k_dir_boundary<T, PC>), grid_for(c, 2 * g.plane), 256, g, c->codes, zr,
+                 P(sold), P(snew), c->sc, par);
+          if ((rc = exchange_halo(c, snew, sizeof(T), nccl_real(c), 1))) return rc;
+        }
+        const bool prof = c->profile_iters > 0 && it <= c->profile_iters;
+        if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1)], c->stream));
+        LAUNCH(c, (k_phaseA<T, VEC, PC>), gridA, blockA, g, c->codes, zr, P(sold), P(snew),
+               P(c->q), c->sc, c->partials, par, zc);
+        if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 1], c->stream));
+        if ((rc = gather_slots(c, c->sc->gA, 1))) return rc;
+        if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 2], c->stream));
+        LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->p), P(c->r),
+               P(snew), P(c->q), P(c->z), c->sc, c->partials, par, 0);
+        if (prof) CU(cudaEventRecord(c->pev[3 * c->profile_iters + (it - 1)], c->stream));
+        if ((rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
+        std::swap(sold, snew);
+      }
+      CU(cudaGetLastError());
+      if (c->fixed_iters > 0 && it < limit) continue;
+      CU(cudaMemcpyAsync(&c->hsc->done, &c->sc->done, sizeof(int), cudaMemcpyDeviceToHost,
+                         c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      done = c->hsc->done != 0;
+    }
+    LAUNCH(c, k_finalize, 1, 1, c->sc, it & 1);
+    CU(cudaGetLastError());
+    return SPL_OK;
+  }
+
+  static int pcg_dispatch(spl_ctx* c) {
+    const int pc = c->d.precond;
+    if (c->vec == 4) {
+      if (pc == SPL_PC_NONE) return pcg<4, PC_NONE>(c);
+      if (pc == SPL_PC_JACOBI) return pcg<4, PC_JACOBI>(c);
+    } else {
+      if (pc == SPL_PC_NONE) return pcg<1, PC_NONE>(c);
+      if (pc == SPL_PC_JACOBI) return pcg<1, PC_JACOBI>(c);
+    }
+    return fail(c, SPL_E_BADARG, "preconditioner %d is not available", pc);
+  }
+
+  static int grad(spl_ctx* c, double dt) {
+    const Geo& g = c->g;
+    int rc = exchange_halo(c, c->p, sizeof(T), nccl_real(c), 1);
+    if (rc) return rc;
+    const T kappa = T(dt / (c->d.h * c->d.rho));
+    LAUNCH(c, k_grad_sub<T>, grid_for(c, g.ncell), 256, g, c->media, P(c->p), P(c->u),
+           P(c->v), P(c->w), kappa);
+    CU(cudaGetLastError());
+    return SPL_OK;
+  }
+
+  static int check(spl_ctx* c) {
+    const Geo& g = c->g;
+    int rc = exchange_velocity(c, 1);
+    if (rc) return rc;
+    LAUNCH(c, k_check<T>, grid_for(c, g.ncell), 256, g, c->codes, P(c->u), P(c->v), P(c->w),
+           P(c->p), c->sc, c->partials);
+    CU(cudaGetLastError());
+    return gather_slots(c, c->sc->gD, 1);
+  }
+};
+
+#define DISPATCH(c, expr_f32, expr_f64) ((c)->d.dtype == SPL_F64 ? (expr_f64) : (expr_f32))
+
+int do_rhs(spl_ctx* c, double dt) {
+  const double scale = (c->d.h * c->d.rho) / dt;   // Pressure.fs:64
+  int rc = DISPATCH(c, Impl<float>::rhs(c, (float)scale, c->r),
+                    Impl<double>::rhs(c, scale, c->r));
+  if (rc) return rc;
+  c->have_rhs = true;
+  c->rhs_dt = dt;
+  return SPL_OK;
+}
+
+float ev_ms(spl_ctx* c, int a, int b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]);
+  return ms;
+}
+
+// fill info from the device scalars after a solve / check
+int read_back(spl_ctx* c, spl_info* info, bool solve, bool chk) {
+  int rc = pull_scal(c);
+  if (rc) return rc;
+  const Scal* h = c->hsc;
+  if (!info) return SPL_OK;
+  if (solve) {
+    info->iters = h->iters;
+    info->converged = h->converged;
+    info->r_inf = h->rmax;
+    info->b_inf = h->bmax;
+  }
+  if (chk) {
+    double m = 0.0;
+    for (int w = 0; w < c->d.world; ++w) m = fmax(m, h->gD[w]);
+    info->max_abs_div = m;
+    info->nonfinite = (int64_t)h->nonfinite;
+  }
+  info->trace_escapes = (int64_t)h->escapes;
+  info->kernel_launches = c->launches;
+  return SPL_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int spl_abi_version(void) { return SPL_ABI_VERSION; }
+
+int spl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void spl_desc_default(spl_desc* d) {
+  if (!d) return;
+  memset(d, 0, sizeof *d);
+  d->nx = d->ny = d->nz = 1;
+  d->h = 10.0;                 // Constants.fs:11
+  d->rho = 999.97;             // Constants.fs:15
+  d->dtype = SPL_F32;
+  d->precond = SPL_PC_JACOBI;
+  d->tol = 1e-6;
+  d->max_iters = 20000;
+  d->tau = 0.0;
+  d->quirks = 0;
+  d->device = 0;
+  d->rank = 0;
+  d->world = 1;
+  d->nz_global = 0;
+  d->z0 = 0;
+  d->nccl_id = nullptr;
+  d->gravity[0] = 0.0;         // Constants.fs:26
+  d->gravity[1] = -9.81;
+  d->gravity[2] = 0.0;
+}
+
+const char* spl_last_error(const spl_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int spl_nccl_unique_id(void* out128) {
+  spl_ctx* c = nullptr;
+  std::string err;
+  if (!out128) return fail(c, SPL_E_BADARG, "out128 is NULL");
+  if (!load_nccl(err)) return fail(c, SPL_E_CUDA, "%s", err.c_str());
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return SPL_OK;
+}
+
+void spl_destroy(spl_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->d.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  for (void* p : c->alloc)
+    if (p) cudaFree(p);
+  if (c->sc) cudaFree(c->sc);
+  if (c->partials) cudaFree(c->partials);
+  if (c->flag) cudaFree(c->flag);
+  if (c->hsc) cudaFreeHost(c->hsc);
+  if (c->hflag) cudaFreeHost(c->hflag);
+  for (cudaEvent_t e : c->ev)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->tev)
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+static int create_impl(spl_ctx* c, const spl_desc* desc) {
+  c->d = *desc;
+  spl_desc& d = c->d;
+  if (d.nx < 1 || d.ny < 1 || d.nz < 1)
+    return fail(c, SPL_E_BADARG, "box %d x %d x %d is empty", d.nx, d.ny, d.nz);
+  if (d.dtype != SPL_F32 && d.dtype != SPL_F64)
+    return fail(c, SPL_E_BADARG, "dtype %d is neither SPL_F32 nor SPL_F64", d.dtype);
+  if (!(d.h > 0.0) || !(d.rho > 0.0))
+    return fail(c, SPL_E_BADARG, "h and rho must be positive");
+  if (d.world < 1) d.world = 1;
+  if (d.world > MAXW) return fail(c, SPL_E_BADARG, "world %d exceeds %d", d.world, MAXW);
+  if (d.rank < 0 || d.rank >= d.world)
+    return fail(c, SPL_E_BADARG, "rank %d outside world %d", d.rank, d.world);
+  if (d.nz_global <= 0) d.nz_global = d.nz;
+  if (d.world == 1) { d.z0 = 0; d.nz_global = d.nz; }
+  if (d.z0 < 0 || d.z0 + d.nz > d.nz_global)
+    return fail(c, SPL_E_BADARG, "slab [%d,%d) outside nz_global %d", d.z0, d.z0 + d.nz,
+                d.nz_global);
+  if (d.max_iters < 0) d.max_iters = 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(c, SPL_E_CUDA, "no CUDA device: libsplashy_cuda has no CPU fallback");
+  if (d.device < 0 || d.device >= ndev)
+    return fail(c, SPL_E_BADARG, "device %d of %d", d.device, ndev);
+  CU(cudaSetDevice(d.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, d.device));
+  c->sms = prop.multiProcessorCount;
+  c->esz = d.dtype == SPL_F64 ? 8 : 4;
+  c->vec = (d.nx % 4 == 0) ? 4 : 1;
+  Geo& g = c->g;
+  g.nx = d.nx; g.ny = d.ny; g.nz = d.nz;
+  g.hz = d.world > 1 ? 4 : 1;
+  g.z0 = d.z0; g.nzg = d.nz_global;
+  g.plane = (long long)d.nx * d.ny;
+  g.ncell = g.plane * d.nz;
+  if (const char* e = getenv("SPL_ZCHUNK")) c->zchunk_override = atoi(e);
+
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& e : c->ev) CU(cudaEventCreate(&e));
+  for (auto& e : c->tev) CU(cudaEventCreate(&e));
+  int rc;
+  char** fields[] = {&c->u, &c->v, &c->w, &c->u2, &c->v2, &c->w2, &c->p, &c->r,
+                     &c->sa, &c->sb, &c->q};
+  for (int i = 0; i < 11; ++i)
+    if ((rc = alloc_field(c, i, c->esz, fields[i], 0))) return rc;
+  if (d.precond == SPL_PC_RBIC0) {
+    if ((rc = alloc_field(c, 11, c->esz, &c->z, 0))) return rc;
+    if ((rc = alloc_field(c, 12, c->esz, &c->einv, 0))) return rc;
+  }
+  char* tmp;
+  if ((rc = alloc_field(c, 13, 1, &tmp, 0xFF))) return rc;   // SPL_ABSENT everywhere
+  c->media = reinterpret_cast<uint8_t*>(tmp);
+  if ((rc = alloc_field(c, 14, 1, &tmp, 0))) return rc;
+  c->codes = reinterpret_cast<uint8_t*>(tmp);
+  CU(cudaMalloc(&c->sc, sizeof(Scal)));
+  CU(cudaMemsetAsync(c->sc, 0, sizeof(Scal), c->stream));
+  CU(cudaMalloc(&c->partials, sizeof(double) * 2 * MAX_PARTIALS));
+  CU(cudaMalloc(&c->flag, sizeof(int)));
+  CU(cudaHostAlloc(&c->hsc, sizeof(Scal), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&c->hflag, sizeof(int), cudaHostAllocDefault));
+
+  if (d.world > 1) {
+    std::string err;
+    if (!d.nccl_id) return fail(c, SPL_E_BADARG, "world > 1 needs desc.nccl_id");
+    if (!load_nccl(err)) return fail(c, SPL_E_CUDA, "%s", err.c_str());
+    ncclUniqueId id;
+    memcpy(&id, d.nccl_id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, d.world, id, d.rank));
+  }
+  c->d.nccl_id = nullptr;   // caller-owned bytes are not kept
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
+}
+
+int spl_create(spl_ctx** out, const spl_desc* desc) {
+  spl_ctx* none = nullptr;
+  if (!out || !desc) return fail(none, SPL_E_BADARG, "spl_create: NULL argument");
+  *out = nullptr;
+  spl_ctx* c = new spl_ctx();
+  const int rc = create_impl(c, desc);
+  if (rc != SPL_OK) {
+    g_create_error = c->err;
+    spl_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return SPL_OK;
+}
+
+int spl_upload(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
+               const void* w, const void* p) {
+  if (!c) return SPL_E_BADARG;
+  if (!media) return fail(c, SPL_E_BADARG, "spl_upload: media is required");
+  CU(cudaSetDevice(c->d.device));
+  const Geo& g = c->g;
+  const size_t nb = (size_t)g.ncell * c->esz;
+  CU(cudaMemcpyAsync(c->media, media, (size_t)g.ncell, cudaMemcpyHostToDevice, c->stream));
+  const void* src[4] = {u, v, w, p};
+  char* dst[4] = {c->u, c->v, c->w, c->p};
+  for (int i = 0; i < 4; ++i) {
+    if (src[i]) CU(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyHostToDevice, c->stream));
+    else CU(cudaMemsetAsync(dst[i], 0, nb, c->stream));
+  }
+  int rc = exchange_halo(c, reinterpret_cast<char*>(c->media), 1, ncclUint8, g.hz);
+  if (rc) return rc;
+  LAUNCH(c, k_codes, grid_for(c, g.ncell), 256, g, c->media, c->codes);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  c->uploaded = true;
+  c->have_rhs = false;
+  return SPL_OK;
+}
+
+int spl_download(spl_ctx* c, void* u, void* v, void* w, void* p, void* div) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_download before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  const size_t nb = (size_t)c->g.ncell * c->esz;
+  void* dst[4] = {u, v, w, p};
+  char* src[4] = {c->u, c->v, c->w, c->p};
+  for (int i = 0; i < 4; ++i)
+    if (dst[i]) CU(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyDeviceToHost, c->stream));
+  if (div) {
+    int rc = DISPATCH(c, Impl<float>::rhs(c, 1.0f, c->q), Impl<double>::rhs(c, 1.0, c->q));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(div, c->q, nb, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
+}
+
+int spl_advect(spl_ctx* c, double dt, spl_info* info) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_advect before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  c->launches = 0;
+  CU(cudaMemsetAsync(&c->sc->escapes, 0, sizeof(unsigned long long), c->stream));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  int rc = DISPATCH(c, Impl<float>::advect(c, dt), Impl<double>::advect(c, dt));
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  CU(cudaMemcpyAsync(c->hflag, c->flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = pull_scal(c))) return rc;
+  c->have_rhs = false;
+  if (info) {
+    memset(info, 0, sizeof *info);
+    info->ms_advect = info->ms_total = ev_ms(c, 0, 1);
+    info->trace_escapes = (int64_t)c->hsc->escapes;
+    info->kernel_launches = c->launches;
+  }
+  if ((c->d.quirks && *c->hflag) || c->hsc->escapes)
+    return fail(c, SPL_E_TRACE, "Backwards particle trace went too far.");   // Convection.fs:65
+  return SPL_OK;
+}
+
+int spl_add_forces(spl_ctx* c, double dt) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_add_forces before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  int rc = DISPATCH(c, Impl<float>::forces(c, dt), Impl<double>::forces(c, dt));
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_rhs = false;
+  return SPL_OK;
+}
+
+int spl_divergence(spl_ctx* c, double dt, spl_info* info) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_divergence before spl_upload");
+  if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
+  CU(cudaSetDevice(c->d.device));
+  c->launches = 0;
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  int rc = do_rhs(c, dt);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (info) {
+    memset(info, 0, sizeof *info);
+    info->ms_rhs = info->ms_total = ev_ms(c, 0, 1);
+    info->kernel_launches = c->launches;
+  }
+  return SPL_OK;
+}
+
+static int project_impl(spl_ctx* c, double dt, spl_info* info, bool with_advect) {
+  if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
+  CU(cudaSetDevice(c->d.device));
+  c->launches = 0;
+  int rc;
+  CU(cudaMemsetAsync(&c->sc->escapes, 0, sizeof(unsigned long long), c->stream));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  if (with_advect) {
+    if ((rc = DISPATCH(c, Impl<float>::advect(c, dt), Impl<double>::advect(c, dt)))) return rc;
+    // escapes are read back with the scalars below; keep them across the pcg reset
+    CU(cudaMemcpyAsync(&c->hsc->escapes, &c->sc->escapes, sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->hflag, c->flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  if ((rc = do_rhs(c, dt))) return rc;
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  unsigned long long escapes = 0;
+  int too_far = 0;
+  if (with_advect) {
+    CU(cudaStreamSynchronize(c->stream));
+    escapes = c->hsc->escapes;
+    too_far = c->d.quirks ? *c->hflag : 0;
+  }
+  if ((rc = DISPATCH(c, Impl<float>::pcg_dispatch(c), Impl<double>::pcg_dispatch(c)))) return rc;
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  if ((rc = DISPATCH(c, Impl<float>::grad(c, dt), Impl<double>::grad(c, dt)))) return rc;
+  CU(cudaEventRecord(c->ev[4], c->stream));
+  if ((rc = DISPATCH(c, Impl<float>::check(c), Impl<double>::check(c)))) return rc;
+  CU(cudaEventRecord(c->ev[5], c->stream));
+  spl_info local;
+  memset(&local, 0, sizeof local);
+  if ((rc = read_back(c, &local, true, true))) return rc;
+  local.trace_escapes = (int64_t)escapes;
+  local.ms_advect = ev_ms(c, 0, 1);
+  local.ms_rhs = ev_ms(c, 1, 2);
+  local.ms_solve = ev_ms(c, 2, 3);
+  local.ms_grad = ev_ms(c, 3, 4);
+  local.ms_total = ev_ms(c, 0, 5);
+  if (info) *info = local;
+  c->have_rhs = false;
+  if (escapes || too_far)
+    return fail(c, SPL_E_TRACE, "Backwards particle trace went too far.");
+  if (c->hsc->breakdown)
+    return fail(c, SPL_E_NONFINITE, "Invalid pressure.");                 // Pressure.fs:138
+  if (!local.converged && c->fixed_iters == 0)
+    return fail(c, SPL_E_NOT_CONVERGED,
+                "PCG stopped after %d iterations with max|r| = %g (max|b| = %g)", local.iters,
+                local.r_inf, local.b_inf);
+  return SPL_OK;
+}
+
+int spl_project(spl_ctx* c, double dt, spl_info* info) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_project before spl_upload");
+  return project_impl(c, dt, info, false);
+}
+
+int spl_step(spl_ctx* c, double dt, spl_info* info) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_step before spl_upload");
+  return project_impl(c, dt, info, true);
+}
+
+int spl_check(spl_ctx* c, double div_tol, spl_info* info) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_check before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  c->launches = 0;
+  CU(cudaMemsetAsync(&c->sc->nonfinite, 0, sizeof(unsigned long long), c->stream));
+  int rc = DISPATCH(c, Impl<float>::check(c), Impl<double>::check(c));
+  if (rc) return rc;
+  spl_info local;
+  memset(&local, 0, sizeof local);
+  if ((rc = read_back(c, &local, false, true))) return rc;
+  if (info) *info = local;
+  if (local.nonfinite)   // Vector.fs:17, Pressure.fs:138-142
+    return fail(c, SPL_E_NONFINITE,
+                "Vector3d has an invalid quantity: either NaN or ±Infinity. (%lld entries)",
+                (long long)local.nonfinite);
+  if (local.max_abs_div > div_tol)   // Pressure.fs:149
+    return fail(c, SPL_E_DIVERGENCE, "Velocity field is not correct: divergence %g.",
+                local.max_abs_div);
+  return SPL_OK;
+}
+
+void* spl_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void spl_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int spl_snapshot(spl_ctx* c) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_snapshot before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  if (!c->have_snapshot) {
+    int rc;
+    if ((rc = alloc_field(c, 15, c->esz * 3, &c->su, 0))) return rc;
+    c->have_snapshot = true;
+  }
+  const size_t nb = (size_t)c->g.ncell * c->esz;
+  const size_t stride = field_bytes(c, c->esz);
+  char* base = static_cast<char*>(c->alloc[15]);
+  CU(cudaMemcpyAsync(base, c->u, nb, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(base + stride, c->v, nb, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(base + 2 * stride, c->w, nb, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
+}
+
+int spl_restore(spl_ctx* c) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->have_snapshot) return fail(c, SPL_E_STATE, "spl_restore before spl_snapshot");
+  CU(cudaSetDevice(c->d.device));
+  const size_t nb = (size_t)c->g.ncell * c->esz;
+  const size_t stride = field_bytes(c, c->esz);
+  char* base = static_cast<char*>(c->alloc[15]);
+  CU(cudaMemcpyAsync(c->u, base, nb, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->v, base + stride, nb, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->w, base + 2 * stride, nb, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_rhs = false;
+  return SPL_OK;
+}
+
+int spl_timer_start(spl_ctx* c) {
+  if (!c) return SPL_E_BADARG;
+  CU(cudaSetDevice(c->d.device));
+  CU(cudaEventRecord(c->tev[0], c->stream));
+  return SPL_OK;
+}
+
+int spl_timer_stop(spl_ctx* c, float* ms) {
+  if (!c || !ms) return SPL_E_BADARG;
+  CU(cudaSetDevice(c->d.device));
+  CU(cudaEventRecord(c->tev[1], c->stream));
+  CU(cudaEventSynchronize(c->tev[1]));
+  CU(cudaEventElapsedTime(ms, c->tev[0], c->tev[1]));
+  return SPL_OK;
+}
+
+int spl_profile_pcg(spl_ctx* c, double dt, int iters, float* ms_a, float* ms_b) {
+  if (!c || !ms_a || !ms_b) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_profile_pcg before spl_upload");
+  if (iters < 1 || iters > 256) return fail(c, SPL_E_BADARG, "iters must be in [1, 256]");
+  if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
+  CU(cudaSetDevice(c->d.device));
+  int rc = do_rhs(c, dt);
+  if (rc) return rc;
+  const int n_ev = 4 * iters;
+  cudaEvent_t* evs = new cudaEvent_t[n_ev];
+  for (int i = 0; i < n_ev; ++i) CU(cudaEventCreate(&evs[i]));
+  c->pev = evs;
+  c->profile_iters = iters;
+  const int keep_fixed = c->fixed_iters;
+  c->fixed_iters = iters;
+  rc = DISPATCH(c, Impl<float>::pcg_dispatch(c), Impl<double>::pcg_dispatch(c));
+  c->fixed_iters = keep_fixed;
+  c->profile_iters = 0;
+  c->pev = nullptr;
+  if (rc == SPL_OK) {
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = SPL_E_CUDA;
+  }
+  double a = 0.0, b = 0.0;
+  if (rc == SPL_OK) {
+    for (int i = 0; i < iters; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, evs[3 * i], evs[3 * i + 1]);
+      a += t;
+      cudaEventElapsedTime(&t, evs[3 * i + 2], evs[3 * iters + i]);
+      b += t;
+    }
+    *ms_a = (float)(a / iters);
+    *ms_b = (float)(b / iters);
+  }
+  for (int i = 0; i < n_ev; ++i) cudaEventDestroy(evs[i]);
+  delete[] evs;
+  c->have_rhs = false;
+  return rc;
+}
+
+int spl_set_fixed_iters(spl_ctx* c, int iters) {
+  if (!c) return SPL_E_BADARG;
+  c->fixed_iters = iters > 0 ? iters : 0;
+  return SPL_OK;
+}
+
+void* spl_device_ptr(spl_ctx* c, int which, int* halo_planes) {
+  if (!c) return nullptr;
+  if (halo_planes) *halo_planes = c->g.hz;
+  switch (which) {
+    case 0: return c->u - (size_t)c->g.hz * c->g.plane * c->esz;
+    case 1: return c->v - (size_t)c->g.hz * c->g.plane * c->esz;
+    case 2: return c->w - (size_t)c->g.hz * c->g.plane * c->esz;
+    case 3: return c->p - (size_t)c->g.hz * c->g.plane * c->esz;
+    case 4: return c->r - (size_t)c->g.hz * c->g.plane * c->esz;
+    case 5: return c->media - (size_t)c->g.hz * c->g.plane;
+    case 6: return c->codes - (size_t)c->g.hz * c->g.plane;
+    default: return nullptr;
+  }
+}
+
+}  // extern "C"
