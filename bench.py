@@ -36,8 +36,8 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "advect+project cell-updates/s"
 UNIT = "cell-updates/s"
-BYTES_PHASE_A = 17     # r 4 + s 4 + code 1 -> s' 4 + q 4            
-BYTES_PHASE_B = 25     # x,r,s,q 16 + code 1 -> x,r 8  (Jacobi)
+BYTES_PHASE_A = 33     # r 4 + s 4 + code 1 + x 8 -> s' 4 + q 4 + x 8 (fp64 x)  
+BYTES_PHASE_B = 13     # r 4 + q 4 + code 1 -> r 4  (Jacobi)
 
 
 def parse_args():
@@ -342,7 +342,7 @@ def run_cuda(args):
                                                   "GBps": gbs_a, "frac": gbs_a / peak},
                                      "k_phaseB": {"ms": ms_b, "bytes_per_cell": BYTES_PHASE_B,
                                                   "GBps": gbs_b, "frac": gbs_b / peak}},
-                         "whole_step": {"bytes_per_cell": 71 + args.pcg_iters * 42,
+                         "whole_step": {"bytes_per_cell": 71 + args.pcg_iters * (BYTES_PHASE_A + BYTES_PHASE_B),
                                         "GBps": step_gbs, "frac": step_gbs / peak}},
             "clocks": clocks,
             "to_tolerance": tol_run,

@@ -224,6 +224,13 @@ int pull_scal(spl_ctx* c) {
 
 __global__ void k_set_bmax(Scal* sc) { sc->bmax = rmax_of(sc, 0); }
 
+template <typename A, typename B>
+__global__ void k_convert(long long n, const A* __restrict__ in, B* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = (B)in[i];
+}
+
 __global__ void k_finalize(Scal* sc, int par_last) {
   if (sc->done) return;
   const double rmax = rmax_of(sc, par_last);
@@ -264,7 +271,8 @@ struct Impl {
              P(c->u2), P(c->v2), P(c->w2), dt, c->sc, c->flag);
     } else {
       const T cc = T(-(dt / c->d.h));
-      LAUNCH(c, k_advect<T>, grid, 256, g, c->media, P(c->u), P(c->v), P(c->w), P(c->u2),
+      const dim3 agrid((g.nx + 31) / 32, (g.ny + 7) / 8, g.nz < 65535 ? g.nz : 65535);
+      LAUNCH(c, k_advect<T>, agrid, dim3(32, 8), g, c->media, P(c->u), P(c->v), P(c->w), P(c->u2),
              P(c->v2), P(c->w2), cc, c->sc);
     }
     CU(cudaGetLastError());
@@ -297,7 +305,7 @@ struct Impl {
     const Geo& g = c->g;
     const size_t fb = field_bytes(c, sizeof(T));
     // x = 0, s = 0 (with halos), q = 0
-    CU(cudaMemsetAsync(c->alloc[6], 0, fb, c->stream));   // p
+    CU(cudaMemsetAsync(c->alloc[6], 0, field_bytes(c, 8), c->stream));   // p (fp64)
     CU(cudaMemsetAsync(c->alloc[8], 0, fb, c->stream));   // sa
     CU(cudaMemsetAsync(c->alloc[9], 0, fb, c->stream));   // sb
     CU(cudaMemsetAsync(c->alloc[10], 0, fb, c->stream));  // q
@@ -323,8 +331,8 @@ struct Impl {
     const T* zr = (PC == PC_RBIC0) ? P(c->z) : P(c->r);
 
     // rho_0 = r.z, max|b|  (phase B with alpha = 0)
-    LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->p), P(c->r), P(c->sa),
-           P(c->q), P(c->z), c->sc, c->partials, 0, 1);
+    LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
+           c->sc, c->partials, 0, 1);
     int rc = gather_slots(c, &c->sc->gBM[0][0][0], 2);
     if (rc) return rc;
     LAUNCH(c, k_set_bmax, 1, 1, c->sc);
@@ -349,12 +357,12 @@ struct Impl {
         const bool prof = c->profile_iters > 0 && it <= c->profile_iters;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1)], c->stream));
         LAUNCH(c, (k_phaseA<T, VEC, PC>), gridA, blockA, g, c->codes, zr, P(sold), P(snew),
-               P(c->q), c->sc, c->partials, par, zc);
+               P(c->q), reinterpret_cast<double*>(c->p), c->sc, c->partials, par, zc);
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 1], c->stream));
         if ((rc = gather_slots(c, c->sc->gA, 1))) return rc;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 2], c->stream));
-        LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->p), P(c->r),
-               P(snew), P(c->q), P(c->z), c->sc, c->partials, par, 0);
+        LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
+               c->sc, c->partials, par, 0);
         if (prof) CU(cudaEventRecord(c->pev[3 * c->profile_iters + (it - 1)], c->stream));
         if ((rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
         std::swap(sold, snew);
@@ -366,6 +374,9 @@ struct Impl {
       CU(cudaStreamSynchronize(c->stream));
       done = c->hsc->done != 0;
     }
+    // the last alpha_K s_K is still pending (phase A adds the previous term)
+    LAUNCH(c, (k_xflush<T, VEC>), gridB, 256, g, reinterpret_cast<double*>(c->p), P(c->sa),
+           P(c->sb), c->sc);
     LAUNCH(c, k_finalize, 1, 1, c->sc, it & 1);
     CU(cudaGetLastError());
     return SPL_OK;
@@ -385,10 +396,11 @@ struct Impl {
 
   static int grad(spl_ctx* c, double dt) {
     const Geo& g = c->g;
-    int rc = exchange_halo(c, c->p, sizeof(T), nccl_real(c), 1);
+    int rc = exchange_halo(c, c->p, 8, ncclDouble, 1);
     if (rc) return rc;
-    const T kappa = T(dt / (c->d.h * c->d.rho));
-    LAUNCH(c, k_grad_sub<T>, grid_for(c, g.ncell), 256, g, c->media, P(c->p), P(c->u),
+    const double kappa = dt / (c->d.h * c->d.rho);
+    LAUNCH(c, k_grad_sub<T>, grid_for(c, g.ncell), 256, g, c->media,
+           reinterpret_cast<const double*>(c->p), P(c->u),
            P(c->v), P(c->w), kappa);
     CU(cudaGetLastError());
     return SPL_OK;
@@ -399,7 +411,7 @@ struct Impl {
     int rc = exchange_velocity(c, 1);
     if (rc) return rc;
     LAUNCH(c, k_check<T>, grid_for(c, g.ncell), 256, g, c->codes, P(c->u), P(c->v), P(c->w),
-           P(c->p), c->sc, c->partials);
+           reinterpret_cast<const double*>(c->p), c->sc, c->partials);
     CU(cudaGetLastError());
     return gather_slots(c, c->sc->gD, 1);
   }
@@ -564,8 +576,8 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   int rc;
   char** fields[] = {&c->u, &c->v, &c->w, &c->u2, &c->v2, &c->w2, &c->p, &c->r,
                      &c->sa, &c->sb, &c->q};
-  for (int i = 0; i < 11; ++i)
-    if ((rc = alloc_field(c, i, c->esz, fields[i], 0))) return rc;
+  for (int i = 0; i < 11; ++i)   // p (slot 6) is always fp64
+    if ((rc = alloc_field(c, i, i == 6 ? 8 : c->esz, fields[i], 0))) return rc;
   if (d.precond == SPL_PC_RBIC0) {
     if ((rc = alloc_field(c, 11, c->esz, &c->z, 0))) return rc;
     if ((rc = alloc_field(c, 12, c->esz, &c->einv, 0))) return rc;
@@ -618,11 +630,21 @@ int spl_upload(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
   const Geo& g = c->g;
   const size_t nb = (size_t)g.ncell * c->esz;
   CU(cudaMemcpyAsync(c->media, media, (size_t)g.ncell, cudaMemcpyHostToDevice, c->stream));
-  const void* src[4] = {u, v, w, p};
-  char* dst[4] = {c->u, c->v, c->w, c->p};
-  for (int i = 0; i < 4; ++i) {
+  const void* src[3] = {u, v, w};
+  char* dst[3] = {c->u, c->v, c->w};
+  for (int i = 0; i < 3; ++i) {
     if (src[i]) CU(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyHostToDevice, c->stream));
     else CU(cudaMemsetAsync(dst[i], 0, nb, c->stream));
+  }
+  // pressure is kept in fp64 on the device
+  if (!p) {
+    CU(cudaMemsetAsync(c->p, 0, (size_t)g.ncell * 8, c->stream));
+  } else if (c->d.dtype == SPL_F64) {
+    CU(cudaMemcpyAsync(c->p, p, (size_t)g.ncell * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CU(cudaMemcpyAsync(c->q, p, nb, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, (k_convert<float, double>), grid_for(c, g.ncell), 256, g.ncell,
+           reinterpret_cast<const float*>(c->q), reinterpret_cast<double*>(c->p));
   }
   int rc = exchange_halo(c, reinterpret_cast<char*>(c->media), 1, ncclUint8, g.hz);
   if (rc) return rc;
@@ -639,10 +661,19 @@ int spl_download(spl_ctx* c, void* u, void* v, void* w, void* p, void* div) {
   if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_download before spl_upload");
   CU(cudaSetDevice(c->d.device));
   const size_t nb = (size_t)c->g.ncell * c->esz;
-  void* dst[4] = {u, v, w, p};
-  char* src[4] = {c->u, c->v, c->w, c->p};
-  for (int i = 0; i < 4; ++i)
+  void* dst[3] = {u, v, w};
+  char* src[3] = {c->u, c->v, c->w};
+  for (int i = 0; i < 3; ++i)
     if (dst[i]) CU(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyDeviceToHost, c->stream));
+  if (p) {
+    if (c->d.dtype == SPL_F64) {
+      CU(cudaMemcpyAsync(p, c->p, nb, cudaMemcpyDeviceToHost, c->stream));
+    } else {   // fp64 accumulator -> fp32 at the boundary
+      LAUNCH(c, (k_convert<double, float>), grid_for(c, c->g.ncell), 256, c->g.ncell,
+             reinterpret_cast<const double*>(c->p), reinterpret_cast<float*>(c->q));
+      CU(cudaMemcpyAsync(p, c->q, nb, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
   if (div) {
     int rc = DISPATCH(c, Impl<float>::rhs(c, 1.0f, c->q), Impl<double>::rhs(c, 1.0, c->q));
     if (rc) return rc;
@@ -905,7 +936,7 @@ void* spl_device_ptr(spl_ctx* c, int which, int* halo_planes) {
     case 0: return c->u - (size_t)c->g.hz * c->g.plane * c->esz;
     case 1: return c->v - (size_t)c->g.hz * c->g.plane * c->esz;
     case 2: return c->w - (size_t)c->g.hz * c->g.plane * c->esz;
-    case 3: return c->p - (size_t)c->g.hz * c->g.plane * c->esz;
+    case 3: return c->p - (size_t)c->g.hz * c->g.plane * 8;   // always fp64
     case 4: return c->r - (size_t)c->g.hz * c->g.plane * c->esz;
     case 5: return c->media - (size_t)c->g.hz * c->g.plane;
     case 6: return c->codes - (size_t)c->g.hz * c->g.plane;

@@ -4,8 +4,15 @@
 // A is never formed; one PCG iteration is two kernels separated by
 // the two global reductions CG needs:
 //
-//   phase A : s' = z + beta s ; q = A s' ; partial s'.q          (17 B/cell)
-//   phase B : x += alpha s' ; r -= alpha q ; partial r.z, max|r| (24 B/cell Jacobi)
+//   phase A(it): s' = z + beta s ; q = A s' ; partial s'.q ;
+//                x += alpha_{it-1} s            (the previous direction, which
+//                                                this kernel reads anyway)
+//   phase B(it): r -= alpha q ; partial r.z, max|r|
+//
+// The pressure accumulator x is always fp64: with fp32 storage its rounding
+// (eps |p|) is what limits the divergence-free residual on 256^3+ grids.
+// fp32 fields: A = r4 + s4 + code1 + x8 -> s'4 + q4 + x8 = 33 B/cell,
+//              B = r4 + q4 + code1 -> r4 = 13 B/cell.
 //
 // HBM-bound; no tensor cores (no dense contraction on this path).
 #pragma once
@@ -39,62 +46,110 @@ __device__ __forceinline__ double rmax_of(const Scal* sc, int slot) {
   return max_slots(&sc->gBM[slot][0][1], sc->world, 2);
 }
 
+// 1/diag lookup: lut[n] = 1/n (correctly rounded), lut[0] = 0; indexed with
+// popc(code & 63) for Fluid cells and 0 otherwise.
+template <typename T>
+__device__ __forceinline__ void fill_inv_lut(T* lut) {
+  const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+  if (tid < 8) lut[tid] = (tid >= 1 && tid <= 6) ? T(1) / T(tid) : T(0);
+}
+__device__ __forceinline__ int lut_index(unsigned code) {
+  return (code & B_FLUID) ? __popc(code & 63u) : 0;
+}
+
 // ---- phase A ---------------------------------------------------------------
 // CTA = 32 x TILE_Y threads; a thread owns VEC consecutive x cells of one row
-// and marches along z keeping the new search direction of planes k-1, k, k+1
-// in registers.  +-x neighbours come from warp shuffles, +-y neighbours are
-// recomputed from L1-resident rows, so every array is pulled from HBM once.
-template <typename T, int VEC, int PC>
-struct PhaseA {
-  const uint8_t* __restrict__ codes;
-  const T* __restrict__ zr;     // z (PC_RBIC0), r (PC_NONE / PC_JACOBI)
-  const T* __restrict__ sold;
-  T* __restrict__ snew;
-  Geo g;
-  T beta;
-
-  __device__ __forceinline__ VecT<T, VEC> dir_vec(long long idx, int k) const {
-    VecT<T, VEC> out;
-    if (k < 0 || k >= g.nz) {
-      // neighbouring slab's plane: already the new direction (halo exchange),
-      // zeros at the global ends
-      return vload<T, VEC>(snew, idx);
-    }
-    const VecT<T, VEC> a = vload<T, VEC>(zr, idx);
-    const VecT<T, VEC> b = vload<T, VEC>(sold, idx);
-    if (PC == PC_JACOBI) {
-      const VecT<uint8_t, VEC> c = cload<VEC>(codes, idx);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e)
-        out.v[e] = a.v[e] * inv_diag<T>(c.v[e]) + beta * b.v[e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) out.v[e] = a.v[e] + beta * b.v[e];
-    }
-    return out;
-  }
-  __device__ __forceinline__ T dir_one(long long idx, int k) const {
-    if (k < 0 || k >= g.nz) return snew[idx];
-    const T a = zr[idx];
-    const T b = sold[idx];
-    if (PC == PC_JACOBI) return a * inv_diag<T>(codes[idx]) + beta * b;
-    return a + beta * b;
-  }
+// and marches along z keeping the new search direction of planes c-1, c, c+1
+// in registers.  +-x neighbours come from warp shuffles, +-y neighbours from a
+// triple-buffered shared-memory tile (one barrier per plane); only the two
+// CTA-edge rows and the CTA-edge lanes recompute a halo value from global
+// memory.  Software pipeline: the raw operands (r, s, codes, x) of plane c+2
+// are requested at the top of iteration c and first touched at the top of
+// iteration c+1, so a whole plane of loads per thread is always in flight.
+// Every array is pulled from HBM once.
+template <typename T, int VEC>
+struct RawV {
+  VecT<T, VEC> a, old;
+  VecT<uint8_t, VEC> code;
+};
+template <typename T>
+struct RawS {
+  T a, old;
+  unsigned code;
 };
 
 template <typename T, int VEC, int PC>
-__global__ void __launch_bounds__(32 * TILE_Y)
+struct DirLoader {
+  const uint8_t* __restrict__ codes;
+  const T* __restrict__ zr;     // z (PC_RBIC0), r (PC_NONE / PC_JACOBI)
+  const T* __restrict__ sold;
+  const T* __restrict__ snew;   // only its z-halo planes are read
+  const T* lut;                 // shared: 1/diag
+  int nz;
+  T beta;
+
+  // planes outside [0, nz) belong to the neighbouring slab: the halo of the s'
+  // buffer already holds the new direction (zeros at the global ends)
+  __device__ __forceinline__ bool remote(int k) const { return k < 0 || k >= nz; }
+
+  __device__ __forceinline__ RawV<T, VEC> load(long long idx, int k) const {
+    RawV<T, VEC> r;
+    if (remote(k)) {
+      r.a = vload<T, VEC>(snew, idx);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { r.old.v[e] = T(0); r.code.v[e] = 0; }
+    } else {
+      r.a = vload<T, VEC>(zr, idx);
+      r.old = vload<T, VEC>(sold, idx);
+      r.code = cload<VEC>(codes, idx);
+    }
+    return r;
+  }
+  __device__ __forceinline__ VecT<T, VEC> combine(const RawV<T, VEC>& r, int k) const {
+    if (remote(k)) return r.a;
+    VecT<T, VEC> out;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const T zz = (PC == PC_JACOBI) ? r.a.v[e] * lut[lut_index(r.code.v[e])] : r.a.v[e];
+      out.v[e] = zz + beta * r.old.v[e];
+    }
+    return out;
+  }
+  __device__ __forceinline__ RawS<T> load1(long long idx, int k) const {
+    RawS<T> r;
+    if (remote(k)) {
+      r.a = snew[idx]; r.old = T(0); r.code = 0;
+    } else {
+      r.a = zr[idx]; r.old = sold[idx]; r.code = codes[idx];
+    }
+    return r;
+  }
+  __device__ __forceinline__ T combine1(const RawS<T>& r, int k) const {
+    if (remote(k)) return r.a;
+    const T zz = (PC == PC_JACOBI) ? r.a * lut[lut_index(r.code)] : r.a;
+    return zz + beta * r.old;
+  }
+};
+
+#ifndef SPL_PHASEA_MINB
+#define SPL_PHASEA_MINB 3     // resident CTAs per SM for fp32 (fp64: one less)
+#endif
+template <typename T, int VEC, int PC>
+__global__ void __launch_bounds__(32 * TILE_Y, (sizeof(T) == 8) ? SPL_PHASEA_MINB - 1 : SPL_PHASEA_MINB)
 k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
          const T* __restrict__ sold, T* __restrict__ snew, T* __restrict__ q,
-         Scal* __restrict__ sc, double* __restrict__ partials, int par,
-         int zchunk) {
+         double* __restrict__ x, Scal* __restrict__ sc, double* __restrict__ partials,
+         int par, int zchunk) {
   __shared__ double red[32];
-  __shared__ double s_beta;
+  __shared__ double s_beta, s_alpha;
   __shared__ int s_stop;
+  __shared__ T lut[8];
+  __shared__ VecT<T, VEC> tile[3][TILE_Y + 2][32];
   const int tid = threadIdx.x + threadIdx.y * 32;
+  fill_inv_lut<T>(lut);
   if (tid == 0) {
     int stop = sc->done;
-    double beta = 0.0;
+    double beta = 0.0, alpha_prev = 0.0;
     if (!stop) {
       const double rho1 = rho_of(sc, par ^ 1);   // rho_{it-1}
       const double rho2 = rho_of(sc, par);       // rho_{it-2}
@@ -113,80 +168,139 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
         }
       } else {
         beta = rho1 / rho2;     // rho2 = +inf before the first iteration
+        // step length of the previous iteration (what phase B(it-1) used)
+        if (sc->count > 0) alpha_prev = rho2 / sum_slots(sc->gA, sc->world);
       }
     }
     s_stop = stop;
     s_beta = beta;
+    s_alpha = alpha_prev;
   }
   __syncthreads();
   if (s_stop) return;
 
-  PhaseA<T, VEC, PC> pa{codes, zr, sold, snew, g, T(s_beta)};
-  const int lane = threadIdx.x;
+  const DirLoader<T, VEC, PC> dl{codes, zr, sold, snew, lut, g.nz, T(s_beta)};
+  const double alpha_prev = s_alpha;
+  const int lane = threadIdx.x, ty = threadIdx.y;
   const int i0 = (blockIdx.x * 32 + lane) * VEC;
-  const int j = blockIdx.y * TILE_Y + threadIdx.y;
+  const int j = blockIdx.y * TILE_Y + ty;
   const bool active = (i0 < g.nx) && (j < g.ny);
   const int kb = blockIdx.z * zchunk;
   const int ke = min(kb + zchunk, g.nz);
-  const long long row = g.nx;
+  const long long row = g.nx, plane = g.plane;
+  // CTA-edge rows recompute the neighbouring row, CTA-edge lanes the x
+  // neighbour owned by the adjacent CTA (memory is always valid thanks to the z
+  // halo planes; values outside the box are masked by the code bits)
+  const bool has_hrow = active && (ty == 0 || ty == TILE_Y - 1);
+  const long long hoff = (ty == 0) ? -row : row;
+  const int hslot = (ty == 0) ? 0 : TILE_Y + 1;
+  const bool has_e = active && ((lane == 0 && i0 > 0) || (lane == 31 && i0 + VEC < g.nx));
+  const long long eoff = (lane == 0) ? -1 : VEC;
 
   VecT<T, VEC> zero;
+  VecT<uint8_t, VEC> czero;
+  VecT<double, VEC> dzero;
 #pragma unroll
-  for (int e = 0; e < VEC; ++e) zero.v[e] = T(0);
+  for (int e = 0; e < VEC; ++e) { zero.v[e] = T(0); czero.v[e] = 0; dzero.v[e] = 0.0; }
 
   double acc = 0.0;
   long long idx = ((long long)kb * g.ny + j) * row + i0;
-  VecT<T, VEC> sm = zero, scur = zero, sp = zero;
+  VecT<T, VEC> sm = zero, scur = zero, sp = zero, oldc = zero;
+  VecT<uint8_t, VEC> codec = czero;
+  VecT<double, VEC> xc = dzero, xn = dzero;
+  RawV<T, VEC> raw{zero, zero, czero}, hraw{zero, zero, czero};
+  RawS<T> eraw{T(0), T(0), 0u};
+  T leftc = T(0), rightc = T(0);
+
+  // ---- prologue: planes kb-1 and kb combined, plane kb+1 requested ----------
   if (active) {
-    sm = pa.dir_vec(idx - g.plane, kb - 1);
-    scur = pa.dir_vec(idx, kb);
-  }
-  for (int k = kb; k < ke; ++k, idx += g.plane) {
-    VecT<T, VEC> sym = zero, syp = zero;
-    VecT<uint8_t, VEC> code;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) code.v[e] = 0;
-    T left = T(0), right = T(0);
-    if (active) {
-      sp = pa.dir_vec(idx + g.plane, k + 1);
-      // rows j-1 / j+1: memory is always valid (z halo planes), values are
-      // masked by the code bits when the neighbour is outside the box
-      sym = pa.dir_vec(idx - row, k);
-      syp = pa.dir_vec(idx + row, k);
-      code = cload<VEC>(codes, idx);
-      // CTA-edge lanes fetch the x neighbour owned by the adjacent CTA
-      if (lane == 0 && i0 > 0) left = pa.dir_one(idx - 1, k);
-      if (lane == 31 && i0 + VEC < g.nx) right = pa.dir_one(idx + VEC, k);
+    sm = dl.combine(dl.load(idx - plane, kb - 1), kb - 1);
+    const RawV<T, VEC> r0 = dl.load(idx, kb);
+    scur = dl.combine(r0, kb);
+    oldc = r0.old;
+    codec = r0.code;
+    tile[kb % 3][ty + 1][lane] = scur;
+    if (has_hrow) tile[kb % 3][hslot][lane] = dl.combine(dl.load(idx + hoff, kb), kb);
+    if (has_e) {
+      const T e = dl.combine1(dl.load1(idx + eoff, kb), kb);
+      if (lane == 0) leftc = e; else rightc = e;
     }
+    xc = vload<double, VEC>(x, idx);
+    raw = dl.load(idx + plane, kb + 1);
+    if (kb + 1 < ke) {
+      if (has_hrow) hraw = dl.load(idx + plane + hoff, kb + 1);
+      if (has_e) eraw = dl.load1(idx + plane + eoff, kb + 1);
+      xn = vload<double, VEC>(x, idx + plane);
+    }
+  }
+
+  for (int c = kb; c < ke; ++c, idx += plane) {
+    const int tb = c % 3, tn = (c + 1) % 3;
+    VecT<T, VEC> oldn = zero;
+    VecT<uint8_t, VEC> coden = czero;
+    T leftn = T(0), rightn = T(0);
+    if (active) {
+      // plane c+1: operands were requested one iteration ago
+      sp = dl.combine(raw, c + 1);
+      oldn = raw.old;
+      coden = raw.code;
+      if (c + 1 < ke) {
+        tile[tn][ty + 1][lane] = sp;
+        if (has_hrow) tile[tn][hslot][lane] = dl.combine(hraw, c + 1);
+        if (has_e) {
+          const T e = dl.combine1(eraw, c + 1);
+          if (lane == 0) leftn = e; else rightn = e;
+        }
+      }
+      // request plane c+2
+      if (c + 2 <= ke) raw = dl.load(idx + 2 * plane, c + 2);
+      if (c + 2 < ke) {
+        if (has_hrow) hraw = dl.load(idx + 2 * plane + hoff, c + 2);
+        if (has_e) eraw = dl.load1(idx + 2 * plane + eoff, c + 2);
+      }
+    }
+    __syncthreads();   // tile[tb] (plane c) was completed before the previous barrier
     const T lsh = __shfl_up_sync(0xffffffffu, scur.v[VEC - 1], 1);
     const T rsh = __shfl_down_sync(0xffffffffu, scur.v[0], 1);
-    if (lane != 0) left = lsh;
-    if (lane != 31) right = rsh;
+    const T left = (lane != 0) ? lsh : leftc;
+    const T right = (lane != 31) ? rsh : rightc;
     if (active) {
+      const VecT<T, VEC> sym = tile[tb][ty][lane];
+      const VecT<T, VEC> syp = tile[tb][ty + 2][lane];
       VecT<T, VEC> qv;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        const unsigned c = code.v[e];
+        const unsigned cc = codec.v[e];
         const T s0 = scur.v[e];
         const T xm = (e > 0) ? scur.v[e > 0 ? e - 1 : 0] : left;
         const T xp = (e < VEC - 1) ? scur.v[e < VEC - 1 ? e + 1 : 0] : right;
         // Pressure.fs:44-55: N_i s_i - sum over Fluid neighbours (s = 0 on Air)
         T a = T(0);
-        a += (c & B_XM) ? (s0 - xm) : T(0);
-        a += (c & B_XP) ? (s0 - xp) : T(0);
-        a += (c & B_YM) ? (s0 - sym.v[e]) : T(0);
-        a += (c & B_YP) ? (s0 - syp.v[e]) : T(0);
-        a += (c & B_ZM) ? (s0 - sm.v[e]) : T(0);
-        a += (c & B_ZP) ? (s0 - sp.v[e]) : T(0);
-        a = (c & B_FLUID) ? a : T(0);
+        a += (cc & B_XM) ? (s0 - xm) : T(0);
+        a += (cc & B_XP) ? (s0 - xp) : T(0);
+        a += (cc & B_YM) ? (s0 - sym.v[e]) : T(0);
+        a += (cc & B_YP) ? (s0 - syp.v[e]) : T(0);
+        a += (cc & B_ZM) ? (s0 - sm.v[e]) : T(0);
+        a += (cc & B_ZP) ? (s0 - sp.v[e]) : T(0);
+        a = (cc & B_FLUID) ? a : T(0);
         qv.v[e] = a;
         acc += (double)s0 * (double)a;
       }
       vstore<T, VEC>(q, idx, qv);
       vstore<T, VEC>(snew, idx, scur);
+      // x += alpha_{it-1} * s_{it-1}  (fp64 accumulator, requested >= 1 plane ago)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) xc.v[e] += alpha_prev * (double)oldc.v[e];
+      vstore<double, VEC>(x, idx, xc);
     }
     sm = scur;
     scur = sp;
+    oldc = oldn;
+    codec = coden;
+    leftc = leftn;
+    rightc = rightn;
+    xc = xn;
+    if (active && c + 2 < ke) xn = vload<double, VEC>(x, idx + 2 * plane);
   }
 
   const double bs = block_sum(acc, red);
@@ -199,9 +313,6 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
     if (tid == 0) sc->gA[sc->rank] = t;
   }
 }
-
-// The right-most active lane of a ragged row shuffles a 0 from its inactive
-// neighbour; the value is masked because that cell's B_XP bit is clear.
 
 // ---- boundary planes of the new direction (world > 1) ----------------------
 // Computes s' on local planes 0 and nz-1 so they can be sent to the z
@@ -233,14 +344,15 @@ __global__ void k_dir_boundary(Geo g, const uint8_t* __restrict__ codes,
 // init != 0: alpha forced to 0 (used once per solve to produce rho_0, max|b|).
 template <typename T, int VEC, int PC>
 __global__ void __launch_bounds__(256)
-k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ x,
-         T* __restrict__ r, const T* __restrict__ s, const T* __restrict__ q,
-         const T* __restrict__ z, Scal* __restrict__ sc,
+k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
+         const T* __restrict__ q, const T* __restrict__ z, Scal* __restrict__ sc,
          double* __restrict__ partials, int par, int init) {
   __shared__ double red[32];
   __shared__ double s_alpha;
+  __shared__ T lut[8];
   const int tid = threadIdx.x;
   if (sc->done) return;
+  fill_inv_lut<T>(lut);
   if (tid == 0) {
     double alpha = 0.0;
     if (!init) {
@@ -260,15 +372,9 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ x,
     const long long idx = t * VEC;
     VecT<T, VEC> rv = vload<T, VEC>(r, idx);
     if (!init) {
-      VecT<T, VEC> xv = vload<T, VEC>(x, idx);
-      const VecT<T, VEC> sv = vload<T, VEC>(s, idx);
       const VecT<T, VEC> qv = vload<T, VEC>(q, idx);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        xv.v[e] += alpha * sv.v[e];
-        rv.v[e] -= alpha * qv.v[e];
-      }
-      vstore<T, VEC>(x, idx, xv);
+      for (int e = 0; e < VEC; ++e) rv.v[e] -= alpha * qv.v[e];
       vstore<T, VEC>(r, idx, rv);
     }
     VecT<uint8_t, VEC> c;
@@ -276,7 +382,7 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ x,
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const double rr = (double)rv.v[e];
-      if (PC == PC_JACOBI) rz += rr * (double)(rv.v[e] * inv_diag<T>(c.v[e]));
+      if (PC == PC_JACOBI) rz += rr * (double)(rv.v[e] * lut[lut_index(c.v[e])]);
       if (PC == PC_NONE) rz += rr * rr;
       // PC_RBIC0: r.z is produced by the preconditioner sweep
       const double ar = fabs(rr);
@@ -310,6 +416,31 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ x,
       sc->gBM[par][rank][1] = nanf ? kNaN : m;
       if (!init) sc->count = sc->count + 1;
     }
+  }
+}
+
+// ---- last pending x update ----------------------------------------------------
+// Phase A(it) adds alpha_{it-1} s_{it-1}; when the loop ends after K iterations
+// the last term alpha_K s_K is still pending.  s_K sits in buffer sb for odd K
+// and sa for even K (ping-pong), alpha_K = rho_{K-1} / (s_K . q_K).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+k_xflush(Geo g, double* __restrict__ x, const T* __restrict__ sa, const T* __restrict__ sb,
+         const Scal* __restrict__ sc) {
+  const int K = sc->count;
+  if (K <= 0) return;
+  const T* __restrict__ s = (K & 1) ? sb : sa;
+  const double alpha = rho_of(sc, (K - 1) & 1) / sum_slots(sc->gA, sc->world);
+  if (!(fabs(alpha) <= 1.7976931348623157e308)) return;
+  const long long nq = g.ncell / VEC;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nq;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long idx = t * VEC;
+    const VecT<T, VEC> sv = vload<T, VEC>(s, idx);
+    VecT<double, VEC> xv = vload<double, VEC>(x, idx);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) xv.v[e] += alpha * (double)sv.v[e];
+    vstore<double, VEC>(x, idx, xv);
   }
 }
 

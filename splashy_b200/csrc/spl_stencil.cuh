@@ -74,8 +74,8 @@ k_div_rhs(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ u,
 // velocity 0; every other face is left alone.
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_grad_sub(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ p,
-           T* __restrict__ u, T* __restrict__ v, T* __restrict__ w, T kappa) {
+k_grad_sub(Geo g, const uint8_t* __restrict__ media, const double* __restrict__ p,
+           T* __restrict__ u, T* __restrict__ v, T* __restrict__ w, double kappa) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
        idx += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(idx % g.nx);
@@ -85,7 +85,7 @@ k_grad_sub(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ p,
     const int kg = k + g.z0;
     const uint8_t m0 = media[idx];
     const bool ns0 = is_nonsolid(m0), fl0 = (m0 == FLUID);
-    const T p0 = fl0 ? p[idx] : T(0);
+    const double p0 = fl0 ? p[idx] : 0.0;
     const bool inb[3] = {i < g.nx - 1, j < g.ny - 1, kg < g.nzg - 1};
     const long long off[3] = {1, (long long)g.nx, g.plane};
     T* f[3] = {u, v, w};
@@ -94,8 +94,9 @@ k_grad_sub(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ p,
       const uint8_t m1 = inb[a] ? media[idx + off[a]] : ABSENT;
       const bool ns1 = is_nonsolid(m1), fl1 = (m1 == FLUID);
       if (ns0 && ns1 && (fl0 || fl1)) {
-        const T p1 = fl1 ? p[idx + off[a]] : T(0);
-        f[a][idx] = f[a][idx] - kappa * (p1 - p0);
+        // the pressure difference is formed in fp64 (p is the fp64 accumulator)
+        const double p1 = fl1 ? p[idx + off[a]] : 0.0;
+        f[a][idx] = (T)((double)f[a][idx] - kappa * (p1 - p0));
       } else if ((fl0 && !ns1) || (!ns0 && fl1)) {
         f[a][idx] = T(0);
       }
@@ -109,7 +110,7 @@ k_grad_sub(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ p,
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_check(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ u,
-        const T* __restrict__ v, const T* __restrict__ w, const T* __restrict__ p,
+        const T* __restrict__ v, const T* __restrict__ w, const double* __restrict__ p,
         Scal* __restrict__ sc, double* __restrict__ partials) {
   __shared__ double red[32];
   double mx = 0.0;
@@ -122,7 +123,7 @@ k_check(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ u,
     bad += !isfinite((double)b);
     bad += !isfinite((double)d);
     if (c & B_FLUID) {
-      bad += !isfinite((double)p[idx]);
+      bad += !isfinite(p[idx]);
       const double dv = fabs((double)cell_divergence<T>(g, c, idx, u, v, w));
       if (dv == dv) mx = fmax(mx, dv);
     }

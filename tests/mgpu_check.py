@@ -1,0 +1,114 @@
+"""Multi-GPU (z-slab) parity check, run under torchrun on a GPU box:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+      --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+
+Every rank owns one z-slab of a global box, runs the step through the C ABI
+(NCCL halo exchange + allgather of the CG scalars inside the library), and
+rank 0 compares the gathered result with (a) the same box solved on one GPU and
+(b) the CPU oracle.  Prints one JSON line; exit code 1 on mismatch.
+"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from oracle import dense_ref as dr  # noqa: E402
+from splashy_b200 import Solver, nccl_unique_id, scenes  # noqa: E402
+from splashy_b200.slab import SlabPlan  # noqa: E402
+
+
+def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=False):
+    plan = SlabPlan(nzg, world, uneven=uneven)
+    z0, nz = plan.z0(rank), plan.nz(rank)
+    whole = scenes.vortex(nx, ny, nzg, cfl=2.0, dtype=dtype)
+    part = scenes.slab_of(whole, z0, nz)
+    dt = whole["dt"]
+    tol = 1e-6 if dtype == np.float32 else 1e-10
+    with Solver(nx, ny, nz, dtype=dtype, tol=tol, device=local, rank=rank, world=world,
+                nz_global=nzg, z0=z0, nccl_id=nid) as s:
+        s.upload(part["labels"], part["U"], part["V"], part["W"])
+        if fixed:
+            s.set_fixed_iters(fixed)
+        info = s.step(dt)
+        got = s.download()
+    # gather slabs on rank 0 (gloo-free: through NCCL on torch tensors)
+    out = {}
+    for k in "UVWP":
+        t = torch.from_numpy(np.ascontiguousarray(got[k])).cuda()
+        if rank == 0:
+            bufs = [torch.empty((plan.nz(r), ny, nx), dtype=t.dtype, device="cuda")
+                    for r in range(world)]
+            bufs[0].copy_(t)
+            for r in range(1, world):
+                dist.recv(bufs[r], src=r)
+            out[k] = torch.cat(bufs, 0).cpu().numpy()
+        else:
+            dist.send(t, dst=0)
+    res = None
+    if rank == 0:
+        with Solver(nx, ny, nzg, dtype=dtype, tol=tol, device=local) as s1:
+            s1.upload(whole["labels"], whole["U"], whole["V"], whole["W"])
+            if fixed:
+                s1.set_fixed_iters(fixed)
+            info1 = s1.step(dt)
+            one = s1.download()
+        f64 = [whole[k].astype(np.float64) for k in "UVW"]
+        U1, V1, W1 = dr.advect(whole["labels"], *f64, dt, whole["h"])
+        U2, V2, W2, P2, oinfo = dr.project(whole["labels"], U1, V1, W1, dt, whole["h"],
+                                           whole["rho"], tol=1e-10,
+                                           fixed_iters=fixed or None)
+        vs = max(np.abs(a).max() for a in (U2, V2, W2))
+        err_one = max(float(np.abs(out[k] - one[k]).max()) for k in "UVW") / vs
+        err_orc = max(float(np.abs(out[k] - r).max()) for k, r in
+                      (("U", U2), ("V", V2), ("W", W2))) / vs
+        perr = float(np.abs(out["P"] - one["P"]).max() / max(1e-30, np.abs(one["P"]).max()))
+        lim = 2e-4 if dtype == np.float32 else 1e-8
+        ok = (err_orc <= lim and err_one <= lim and abs(info["iters"] - info1["iters"]) <= 2
+              and info["max_abs_div"] <= (1e-4 if dtype == np.float32 else 1e-8) * vs)
+        if fixed:
+            ok = err_one <= lim and info["iters"] == fixed
+        res = {"case": name, "ok": bool(ok), "world": world, "iters_slab": info["iters"],
+               "iters_one_gpu": info1["iters"], "iters_oracle": oinfo["iters"],
+               "vel_err_vs_one_gpu": err_one, "vel_err_vs_oracle": err_orc,
+               "p_err_vs_one_gpu": perr, "max_abs_div": info["max_abs_div"],
+               "uneven": uneven}
+    return res
+
+
+def main():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    results = []
+    cases = [("vortex_f32", 64, 48, 16 * world, np.float32, 0, False),
+             ("vortex_f64", 36, 20, 12 * world, np.float64, 0, False),
+             ("vortex_f32_fixed", 64, 48, 16 * world, np.float32, 25, False),
+             ("vortex_f64_uneven", 23, 17, 9 * world + 3, np.float64, 0, True)]
+    for name, nx, ny, nzg, dtype, fixed, uneven in cases:
+        box = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        r = run_case(name, nx, ny, nzg, dtype, world, rank, local, box[0], fixed, uneven)
+        if rank == 0:
+            results.append(r)
+        dist.barrier()
+    ok = True
+    if rank == 0:
+        ok = all(r["ok"] for r in results)
+        print(json.dumps({"mgpu_check": "ok" if ok else "FAILED", "results": results}))
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
