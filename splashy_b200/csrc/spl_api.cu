@@ -19,6 +19,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <type_traits>
 
 #include "../../include/splashy_cuda.h"
 #include "spl_advect.cuh"
@@ -115,6 +116,8 @@ struct spl_ctx {
   bool uploaded = false, have_rhs = false, have_snapshot = false;
   int fixed_iters = 0;
   int zchunk_override = 0;
+  int ring_attr_set = 0;
+  bool no_ring = false;        // SPL_NO_RING=1: force the generic phase-A kernel
   int64_t launches = 0;
   double rhs_dt = 0.0;
   std::string err;
@@ -300,6 +303,30 @@ struct Impl {
     return SPL_OK;
   }
 
+  // fp32 / VEC = 4 uses the cp.async ring kernel; every other
+  // combination (fp64, ragged nx) the register-pipelined generic kernel.
+  template <int VEC, int PC>
+  static void launch_phaseA(spl_ctx* c, dim3 gridA, dim3 blockA, const T* zr, const T* sold,
+                            T* snew, int par, int zc) {
+    const Geo& g = c->g;
+    if constexpr (std::is_same<T, float>::value && VEC == 4 && PC != PC_RBIC0) {
+      if (!c->no_ring) {
+        if (!(c->ring_attr_set & (1 << PC))) {   // per context => per device
+          cudaFuncSetAttribute(k_phaseA_ring<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(RingSmem));
+          c->ring_attr_set |= (1 << PC);
+        }
+        k_phaseA_ring<PC><<<gridA, blockA, sizeof(RingSmem), c->stream>>>(
+            g, c->codes, zr, sold, snew, P(c->q), reinterpret_cast<double*>(c->p), c->sc,
+            c->partials, par, zc);
+        c->launches++;
+        return;
+      }
+    }
+    LAUNCH(c, (k_phaseA<T, VEC, PC>), gridA, blockA, g, c->codes, zr, sold, snew, P(c->q),
+           reinterpret_cast<double*>(c->p), c->sc, c->partials, par, zc);
+  }
+
   template <int VEC, int PC>
   static int pcg(spl_ctx* c) {
     const Geo& g = c->g;
@@ -356,8 +383,7 @@ struct Impl {
         }
         const bool prof = c->profile_iters > 0 && it <= c->profile_iters;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1)], c->stream));
-        LAUNCH(c, (k_phaseA<T, VEC, PC>), gridA, blockA, g, c->codes, zr, P(sold), P(snew),
-               P(c->q), reinterpret_cast<double*>(c->p), c->sc, c->partials, par, zc);
+        launch_phaseA<VEC, PC>(c, gridA, blockA, zr, P(sold), P(snew), par, zc);
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 1], c->stream));
         if ((rc = gather_slots(c, c->sc->gA, 1))) return rc;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 2], c->stream));
@@ -569,6 +595,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   g.plane = (long long)d.nx * d.ny;
   g.ncell = g.plane * d.nz;
   if (const char* e = getenv("SPL_ZCHUNK")) c->zchunk_override = atoi(e);
+  if (const char* e = getenv("SPL_NO_RING")) c->no_ring = atoi(e) != 0;
 
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));

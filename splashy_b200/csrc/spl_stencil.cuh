@@ -27,7 +27,9 @@ __global__ void k_codes(Geo g, const uint8_t* __restrict__ media,
     if (j < g.ny - 1 && is_nonsolid(media[idx + g.nx])) c |= B_YP;
     if (kg > 0 && is_nonsolid(media[idx - g.plane])) c |= B_ZM;
     if (kg < g.nzg - 1 && is_nonsolid(media[idx + g.plane])) c |= B_ZP;
-    if (media[idx] == FLUID) c |= B_FLUID;
+    // only Fluid cells (the unknowns) carry a code: every consumer tests the
+    // Fluid bit first, and code == 0 lets popc(code & 63) index the 1/diag table
+    c = (media[idx] == FLUID) ? (c | B_FLUID) : 0u;
     codes[idx] = (uint8_t)c;
   }
 }
