@@ -36,8 +36,11 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "advect+project cell-updates/s"
 UNIT = "cell-updates/s"
-BYTES_PHASE_A = 33     # r 4 + s 4 + code 1 + x 8 -> s' 4 + q 4 + x 8 (fp64 x)  
+NSBUF = int(os.environ.get("SPL_NSBUF", "8"))   # x is flushed every NSBUF iterations
+BYTES_PHASE_A = 17     # r 4 + s 4 + code 1 -> s' 4 + q 4                 
 BYTES_PHASE_B = 13     # r 4 + q 4 + code 1 -> r 4  (Jacobi)
+BYTES_XFLUSH = 4 * NSBUF + 16   # per launch: NSBUF directions + fp64 x read / write
+BYTES_ITER = BYTES_PHASE_A + BYTES_PHASE_B + BYTES_XFLUSH / NSBUF
 
 
 def parse_args():
@@ -284,14 +287,15 @@ def run_cuda(args):
 
     # ---- per-kernel roofline: CUDA events around every PCG launch -------------------------
     s.restore()
-    ms_a, ms_b = s.profile_pcg(dt, 32)
-    ms_a, ms_b = max_over_ranks(ms_a), max_over_ranks(ms_b)
+    ms_a, ms_b, ms_x = s.profile_pcg(dt, 32)
+    ms_a, ms_b, ms_x = max_over_ranks(ms_a), max_over_ranks(ms_b), max_over_ranks(ms_x)
     peak, peak_src = peaks()
     gbs_a = cells_local * BYTES_PHASE_A / (ms_a * 1e-3) / 1e9
     gbs_b = cells_local * BYTES_PHASE_B / (ms_b * 1e-3) / 1e9
+    gbs_x = cells_local * BYTES_XFLUSH / (ms_x * 1e-3) / 1e9 if ms_x > 0 else 0.0
     dom = "k_phaseB" if ms_b >= ms_a else "k_phaseA"
     dom_gbs = gbs_b if dom == "k_phaseB" else gbs_a
-    step_bytes = cells_local * (71 + args.pcg_iters * (BYTES_PHASE_A + BYTES_PHASE_B))
+    step_bytes = cells_local * (71 + args.pcg_iters * BYTES_ITER)
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
 
     # ---- one run-to-tolerance step (iteration count) ------------------------
@@ -341,8 +345,11 @@ def run_cuda(args):
                          "kernels": {"k_phaseA": {"ms": ms_a, "bytes_per_cell": BYTES_PHASE_A,
                                                   "GBps": gbs_a, "frac": gbs_a / peak},
                                      "k_phaseB": {"ms": ms_b, "bytes_per_cell": BYTES_PHASE_B,
-                                                  "GBps": gbs_b, "frac": gbs_b / peak}},
-                         "whole_step": {"bytes_per_cell": 71 + args.pcg_iters * (BYTES_PHASE_A + BYTES_PHASE_B),
+                                                  "GBps": gbs_b, "frac": gbs_b / peak},
+                                     "k_xflush": {"ms": ms_x, "bytes_per_cell": BYTES_XFLUSH,
+                                                  "every_iters": NSBUF, "GBps": gbs_x,
+                                                  "frac": gbs_x / peak}},
+                         "whole_step": {"bytes_per_cell": 71 + args.pcg_iters * BYTES_ITER,
                                         "GBps": step_gbs, "frac": step_gbs / peak}},
             "clocks": clocks,
             "to_tolerance": tol_run,

@@ -157,11 +157,12 @@ int  spl_set_fixed_iters(spl_ctx* ctx, int iters);
 int  spl_timer_start(spl_ctx* ctx);
 int  spl_timer_stop(spl_ctx* ctx, float* ms);
 /* per-kernel timing of the PCG iteration: builds the RHS for dt, then runs
- * `iters` (<= 256) iterations with CUDA events around every phase-A and
- * phase-B launch; returns the average duration of each in milliseconds.  The
- * velocity field is not modified (no gradient subtraction).                   */
+ * `iters` (<= 256) iterations with CUDA events around every phase-A, phase-B
+ * and x-flush launch; returns the average duration of each in milliseconds
+ * (the x flush runs once every SPL_NSBUF = 4 iterations).  The velocity field
+ * is not modified (no gradient subtraction).                                   */
 int  spl_profile_pcg(spl_ctx* ctx, double dt, int iters, float* ms_phase_a,
-                     float* ms_phase_b);
+                     float* ms_phase_b, float* ms_xflush);
 /* device pointer of a field including its z-halo (plumbing for tests):
  * which = 0 u,1 v,2 w,3 p,4 r,5 media,6 codes ; *halo_planes receives hz      */
 void* spl_device_ptr(spl_ctx* ctx, int which, int* halo_planes);

@@ -90,7 +90,7 @@ SYMBOLS = {
     "spl_timer_start": (C.c_int, [_VP]),
     "spl_timer_stop": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "spl_profile_pcg": (C.c_int, [_VP, C.c_double, C.c_int, C.POINTER(C.c_float),
-                                  C.POINTER(C.c_float)]),
+                                  C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "spl_device_ptr": (_VP, [_VP, C.c_int, C.POINTER(C.c_int)]),
 }
 

@@ -55,125 +55,130 @@ __device__ __forceinline__ T sample(const FieldView<T>& F, int bi, int bj, int b
   return total;
 }
 
-// ---- fast path ---------------------------------------------------------------
-// Cells at least ADV_MARGIN away from the x/y box edges whose sample offsets
-// stay within ADV_MARGIN - 1 cells never touch an x/y corner outside the box, so
-// the 8 corners are read with small immediate offsets from the cell's own
-// address.  Only the two z corners are range-tested: planes inside the
-// allocation are read as they are (halo planes at the global ends are zero,
-// which is exactly "absent cell contributes 0"), planes beyond it contribute 0
-// and raise the escape flag when they lie inside the global box.  The kernel is
-// instruction-issue / L1-gather bound, not HBM bound, so the
-// fast path is written for instruction count: 32-bit offsets, lerp form.
-constexpr int ADV_MARGIN = 4;
+// ---- two-pass layout ------------------------------------------------------------
+// k_advect (hot): cells whose whole sampling footprint is provably inside the
+// allocation -- at least ADV_MARGIN cells from the x/y box edges, every RK2 offset
+// within ADV_MAXOFF cells and its z part inside the memory-resident planes (halo
+// planes at the global ends are zero = "absent cell contributes 0") -- are updated with unchecked 8-corner gathers at small
+// immediate offsets from the cell's own address.  Every other Fluid cell is
+// appended to a worklist (warp-aggregated atomic) and finished by k_advect_rest
+// with the fully bounds-tested sampler (box shell, > 3-cell displacements, slab
+// ends), one dense thread per listed cell.  The hot kernel is
+// instruction-issue / L1-gather bound, not HBM bound: it is
+// written for instruction count (32-bit offsets, lerp form, no calls, no stack).
+constexpr int ADV_MARGIN = 4;      // x / y cells from the box edge
+constexpr float ADV_MAXOFF = 2.99f;
 
 template <typename T>
 __device__ __forceinline__ T mix(T a, T b, T w) {   // (1 - w) a + w b
   return fma(w, b, fma(-w, a, a));
 }
 
+// unchecked trilinear sample at (cell + offset); p0 = address of the cell's own
+// value, nx / pl = element strides (pl < 2^31 is guaranteed by the host)
 template <typename T>
-struct FastCtx {
-  int nx, plane;        // element strides (plane < 2^31 is checked on the host)
-  int k;                // local plane of the cell
-  int hlo, hhi;         // planes present in memory
-  int klo, khi;         // planes present in the global box
-};
-
-template <typename T>
-__device__ __forceinline__ T sample_fast(const T* __restrict__ p0, const FastCtx<T>& fc, T ox,
-                                         T oy, T oz, unsigned& escaped) {
+__device__ __forceinline__ T sample_fast(const T* __restrict__ p0, int nx, int pl, T ox, T oy,
+                                         T oz) {
   const T fx = floor(ox), fy = floor(oy), fz = floor(oz);
   const T wx = ox - fx, wy = oy - fy, wz = oz - fz;
-  const int dk = (int)fz;
-  const int ka = fc.k + dk;
-  const bool va = (ka >= fc.hlo) && (ka < fc.hhi);
-  const bool vb = (ka + 1 >= fc.hlo) && (ka + 1 < fc.hhi);
-  if ((!va && ka >= fc.klo && ka < fc.khi) || (!vb && ka + 1 >= fc.klo && ka + 1 < fc.khi))
-    escaped = 1u;
-  const int off = (int)fy * fc.nx + (int)fx;
-  const T* __restrict__ pa = p0 + (off + (va ? dk : 0) * fc.plane);
-  const T* __restrict__ pb = p0 + (off + (vb ? dk + 1 : 0) * fc.plane);
-  const int nx = fc.nx;
-  T A = mix(mix(pa[0], pa[1], wx), mix(pa[nx], pa[nx + 1], wx), wy);
-  T B = mix(mix(pb[0], pb[1], wx), mix(pb[nx], pb[nx + 1], wx), wy);
-  A = va ? A : T(0);
-  B = vb ? B : T(0);
+  const int off = ((int)fz * pl + (int)fy * nx) + (int)fx;
+  const T* __restrict__ pa = p0 + off;
+  const T* __restrict__ pb = pa + pl;
+  const T A = mix(mix(pa[0], pa[1], wx), mix(pa[nx], pa[nx + 1], wx), wy);
+  const T B = mix(mix(pb[0], pb[1], wx), mix(pb[nx], pb[nx + 1], wx), wy);
   return mix(A, B, wz);
 }
 
+// |offset| <= lim in x / y and the z corners [floor(oz + zpad_lo), floor(oz + zpad_hi) + 1]
+// inside the planes present in memory
 template <typename T>
-__device__ __noinline__ T sample_slow(const FieldView<T>& F, int i, int j, int k, T ox, T oy,
-                                      T oz, unsigned* escaped) {
-  unsigned e = 0;
-  const T r = sample(F, i, j, k, ox, oy, oz, e);
-  if (e) *escaped = 1u;
-  return r;
+__device__ __forceinline__ bool within(T a, T b, T c, T lim, T zlo, T zhi, T zpad) {
+  return (fmax(fabs(a), fabs(b)) <= lim) && (c - zpad >= zlo) && (c + zpad < zhi);
 }
 
+// 2-D thread blocks (32 x 8 cells of one plane) keep the gather footprint of a
+// CTA compact in L1; grid = (x tiles, y tiles, planes).
 template <typename T>
-struct AdvectFields {
-  FieldView<T> U, V, W;
-};
-
-// one sample on the fast path with a per-sample fallback for offsets that leave
-// the guaranteed footprint (|offset| > ADV_MARGIN - 1, i.e. CFL > 3)
-template <typename T>
-__device__ __forceinline__ T sample_near(const FieldView<T>& F, const T* __restrict__ p0,
-                                         const FastCtx<T>& fc, int i, int j, T ox, T oy, T oz,
-                                         unsigned& esc) {
-  const T lim = T(ADV_MARGIN - 1);
-  if (fabs(ox) <= lim && fabs(oy) <= lim) return sample_fast(p0, fc, ox, oy, oz, esc);
-  return sample_slow(F, i, j, fc.k, ox, oy, oz, &esc);
+__global__ void __launch_bounds__(256)
+k_advect(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ u,
+         const T* __restrict__ v, const T* __restrict__ w, T* __restrict__ u2,
+         T* __restrict__ v2, T* __restrict__ w2, T c, int* __restrict__ worklist,
+         Scal* __restrict__ sc) {
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  const bool xy_in = (i >= ADV_MARGIN) && (i < g.nx - ADV_MARGIN) && (j >= ADV_MARGIN) &&
+                     (j < g.ny - ADV_MARGIN);
+  const int nx = g.nx, pl = (int)g.plane;
+  const T h = T(0.5), qd = T(0.25);
+  const T lim1 = T(ADV_MAXOFF) - h;     // midpoint offsets get +-1/2 added
+  const T lim2 = T(ADV_MAXOFF);
+  for (int k = blockIdx.z; k < g.nz; k += gridDim.z) {
+    const long long idx = ((long long)k * g.ny + j) * nx + i;
+    const T* __restrict__ pu = u + idx;
+    const T* __restrict__ pv = v + idx;
+    const T* __restrict__ pw = w + idx;
+    T nu = pu[0], nv = pv[0], nw = pw[0];
+    if (media[idx] == FLUID) {
+      // planes reachable from k without leaving the allocation: a sample at z
+      // offset oz touches planes k + floor(oz) and k + floor(oz) + 1
+      const T zlo = -(T)(k + g.hz), zhi = (T)(g.nz + g.hz - 1 - k);
+      bool ok = xy_in;
+      if (ok) {
+        const T u00 = nu, v00 = nv, w00 = nw;
+        // ---- U face at (i + 1/2, j, k): stage 0 = closed-form trilinear weights
+        T v0 = qd * ((pv[-nx] + v00) + (pv[-nx + 1] + pv[1]));
+        T w0 = qd * ((pw[-pl] + w00) + (pw[-pl + 1] + pw[1]));
+        T mx = h * c * u00, my = h * c * v0, mz = h * c * w0;
+        ok = ok && within(mx, my, mz, lim1, zlo, zhi, h);
+        if (ok) {
+          const T u1 = sample_fast(pu, nx, pl, mx, my, mz);
+          const T v1 = sample_fast(pv, nx, pl, mx + h, my - h, mz);
+          const T w1 = sample_fast(pw, nx, pl, mx + h, my, mz - h);
+          const T dx = c * u1, dy = c * v1, dz = c * w1;
+          ok = within(dx, dy, dz, lim2, zlo, zhi, T(0));
+          if (ok) nu = sample_fast(pu, nx, pl, dx, dy, dz);
+        }
+        // ---- V face at (i, j + 1/2, k)
+        if (ok) {
+          const T u0 = qd * ((pu[-1] + pu[nx - 1]) + (u00 + pu[nx]));
+          w0 = qd * ((pw[-pl] + w00) + (pw[-pl + nx] + pw[nx]));
+          mx = h * c * u0; my = h * c * v00; mz = h * c * w0;
+          ok = within(mx, my, mz, lim1, zlo, zhi, h);
+        }
+        if (ok) {
+          const T u1 = sample_fast(pu, nx, pl, mx - h, my + h, mz);
+          const T v1 = sample_fast(pv, nx, pl, mx, my, mz);
+          const T w1 = sample_fast(pw, nx, pl, mx, my + h, mz - h);
+          const T dx = c * u1, dy = c * v1, dz = c * w1;
+          ok = within(dx, dy, dz, lim2, zlo, zhi, T(0));
+          if (ok) nv = sample_fast(pv, nx, pl, dx, dy, dz);
+        }
+        // ---- W face at (i, j, k + 1/2)
+        if (ok) {
+          const T u0 = qd * ((pu[-1] + pu[pl - 1]) + (u00 + pu[pl]));
+          v0 = qd * ((pv[-nx] + pv[pl - nx]) + (v00 + pv[pl]));
+          mx = h * c * u0; my = h * c * v0; mz = h * c * w00;
+          ok = within(mx, my, mz, lim1, zlo, zhi, h);
+        }
+        if (ok) {
+          const T u1 = sample_fast(pu, nx, pl, mx - h, my, mz + h);
+          const T v1 = sample_fast(pv, nx, pl, mx, my - h, mz + h);
+          const T w1 = sample_fast(pw, nx, pl, mx, my, mz);
+          const T dx = c * u1, dy = c * v1, dz = c * w1;
+          ok = within(dx, dy, dz, lim2, zlo, zhi, T(0));
+          if (ok) nw = sample_fast(pw, nx, pl, dx, dy, dz);
+        }
+      }
+      if (!ok) worklist[atomicAdd(&sc->wl_count, 1u)] = (int)idx;   // -> k_advect_rest
+    }
+    u2[idx] = nu;
+    v2[idx] = nv;
+    w2[idx] = nw;
+  }
 }
 
-// interior cell: all three faces.  Stage 0 (velocity at the face centre) uses
-// the closed forms of the trilinear weights (0, 1/2, 1): the component itself
-// and two 4-point averages.
-template <typename T>
-__device__ __forceinline__ void advect_cell_fast(const AdvectFields<T>& f, const FastCtx<T>& fc,
-                                                 int i, int j, long long idx, T c, T out[3],
-                                                 unsigned& esc) {
-  const T* __restrict__ u = f.U.f + idx;
-  const T* __restrict__ v = f.V.f + idx;
-  const T* __restrict__ w = f.W.f + idx;
-  const int nx = fc.nx, pl = fc.plane;
-  const T h = T(0.5), q = T(0.25);
-  // planes k-1 and k+1 are always in memory (hz >= 1)
-  const T u00 = u[0], v00 = v[0], w00 = w[0];
-  {  // U face at (i + 1/2, j, k)
-    const T u0 = u00;
-    const T v0 = q * ((v[-nx] + v00) + (v[-nx + 1] + v[1]));
-    const T w0 = q * ((w[-pl] + w00) + (w[-pl + 1] + w[1]));
-    const T mx = h * c * u0, my = h * c * v0, mz = h * c * w0;
-    const T u1 = sample_near(f.U, u, fc, i, j, mx, my, mz, esc);
-    const T v1 = sample_near(f.V, v, fc, i, j, mx + h, my - h, mz, esc);
-    const T w1 = sample_near(f.W, w, fc, i, j, mx + h, my, mz - h, esc);
-    out[0] = sample_near(f.U, u, fc, i, j, c * u1, c * v1, c * w1, esc);
-  }
-  {  // V face at (i, j + 1/2, k)
-    const T v0 = v00;
-    const T u0 = q * ((u[-1] + u[nx - 1]) + (u00 + u[nx]));
-    const T w0 = q * ((w[-pl] + w00) + (w[-pl + nx] + w[nx]));
-    const T mx = h * c * u0, my = h * c * v0, mz = h * c * w0;
-    const T u1 = sample_near(f.U, u, fc, i, j, mx - h, my + h, mz, esc);
-    const T v1 = sample_near(f.V, v, fc, i, j, mx, my, mz, esc);
-    const T w1 = sample_near(f.W, w, fc, i, j, mx, my + h, mz - h, esc);
-    out[1] = sample_near(f.V, v, fc, i, j, c * u1, c * v1, c * w1, esc);
-  }
-  {  // W face at (i, j, k + 1/2)
-    const T w0 = w00;
-    const T u0 = q * ((u[-1] + u[pl - 1]) + (u00 + u[pl]));
-    const T v0 = q * ((v[-nx] + v[pl - nx]) + (v00 + v[pl]));
-    const T mx = h * c * u0, my = h * c * v0, mz = h * c * w0;
-    const T u1 = sample_near(f.U, u, fc, i, j, mx - h, my, mz + h, esc);
-    const T v1 = sample_near(f.V, v, fc, i, j, mx, my - h, mz + h, esc);
-    const T w1 = sample_near(f.W, w, fc, i, j, mx, my, mz, esc);
-    out[2] = sample_near(f.W, w, fc, i, j, c * u1, c * v1, c * w1, esc);
-  }
-}
-
-// generic face update (box-edge cells): every corner bounds-tested
+// generic face update: every corner bounds-tested
 template <typename T>
 __device__ __forceinline__ T advect_face(const FieldView<T>& U, const FieldView<T>& V,
                                          const FieldView<T>& W, int comp, int i, int j,
@@ -195,51 +200,29 @@ __device__ __forceinline__ T advect_face(const FieldView<T>& U, const FieldView<
   return sample(F, i, j, k, dx, dy, dz, esc);
 }
 
+// second pass: the cells the hot kernel listed (box shell, slab ends, large
+// displacements), one thread per listed cell.
 template <typename T>
-__device__ __noinline__ void advect_cell_edge(const AdvectFields<T>* f, int i, int j, int k,
-                                              T c, T* out, unsigned* esc) {
-  unsigned e = 0;
-  out[0] = advect_face<T>(f->U, f->V, f->W, 0, i, j, k, c, e);
-  out[1] = advect_face<T>(f->U, f->V, f->W, 1, i, j, k, c, e);
-  out[2] = advect_face<T>(f->U, f->V, f->W, 2, i, j, k, c, e);
-  if (e) *esc = 1u;
-}
-
-// 2-D thread blocks (32 x 8 cells of one plane) keep the gather footprint of a
-// CTA compact in L1; grid = (x tiles, y tiles, planes).
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_advect(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ u,
-         const T* __restrict__ v, const T* __restrict__ w, T* __restrict__ u2,
-         T* __restrict__ v2, T* __restrict__ w2, T c, Scal* __restrict__ sc) {
-  AdvectFields<T> f;
-  f.U = FieldView<T>{u, g.nx, g.ny, -g.z0, g.nzg - g.z0, -g.hz, g.nz + g.hz, g.plane};
-  f.V = f.U;
-  f.W = f.U;
-  f.V.f = v;
-  f.W.f = w;
+__global__ void __launch_bounds__(256, 2)
+k_advect_rest(Geo g, const T* __restrict__ u, const T* __restrict__ v,
+              const T* __restrict__ w, T* __restrict__ u2, T* __restrict__ v2,
+              T* __restrict__ w2, T c, const int* __restrict__ worklist,
+              Scal* __restrict__ sc) {
+  FieldView<T> U{u, g.nx, g.ny, -g.z0, g.nzg - g.z0, -g.hz, g.nz + g.hz, g.plane};
+  FieldView<T> V = U, W = U;
+  V.f = v;
+  W.f = w;
   unsigned esc = 0;
-  const int i = blockIdx.x * 32 + threadIdx.x;
-  const int j = blockIdx.y * 8 + threadIdx.y;
-  if (i < g.nx && j < g.ny) {
-    const bool interior = (i >= ADV_MARGIN) && (i < g.nx - ADV_MARGIN) &&
-                          (j >= ADV_MARGIN) && (j < g.ny - ADV_MARGIN);
-    FastCtx<T> fc{g.nx, (int)g.plane, 0, -g.hz, g.nz + g.hz, -g.z0, g.nzg - g.z0};
-    for (int k = blockIdx.z; k < g.nz; k += gridDim.z) {
-      const long long idx = ((long long)k * g.ny + j) * g.nx + i;
-      T nv[3] = {u[idx], v[idx], w[idx]};
-      if (media[idx] == FLUID) {
-        if (interior) {
-          fc.k = k;
-          advect_cell_fast<T>(f, fc, i, j, idx, c, nv, esc);
-        } else {
-          advect_cell_edge<T>(&f, i, j, k, c, nv, &esc);
-        }
-      }
-      u2[idx] = nv[0];
-      v2[idx] = nv[1];
-      w2[idx] = nv[2];
-    }
+  const unsigned n = sc->wl_count;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int idx = worklist[t];
+    const int i = idx % g.nx;
+    const int r = idx / g.nx;
+    const int j = r % g.ny;
+    const int k = r / g.ny;
+    u2[idx] = advect_face<T>(U, V, W, 0, i, j, k, c, esc);
+    v2[idx] = advect_face<T>(U, V, W, 1, i, j, k, c, esc);
+    w2[idx] = advect_face<T>(U, V, W, 2, i, j, k, c, esc);
   }
   if (esc) atomicAdd(&sc->escapes, 1ull);
 }

@@ -97,14 +97,18 @@ struct spl_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6]{};
   cudaEvent_t tev[2]{};        // spl_timer_*
-  cudaEvent_t* pev = nullptr;  // spl_profile_pcg: 3 events per iteration
+  cudaEvent_t* pev = nullptr;  // spl_profile_pcg: 4 events per iteration
+  cudaEvent_t xev[128]{};      // spl_profile_pcg: around the x-flush launches
+  int profile_flushes = 0;
   int profile_iters = 0;       // > 0 while spl_profile_pcg runs
   // fields, allocation start (plane -hz); *_0 = plane 0
-  void* alloc[16]{};
+  void* alloc[32]{};
   char *u = nullptr, *v = nullptr, *w = nullptr;     // current velocity (plane 0)
   char *u2 = nullptr, *v2 = nullptr, *w2 = nullptr;  // advection target
   char *su = nullptr, *sv = nullptr, *sw = nullptr;  // snapshot
-  char *p = nullptr, *r = nullptr, *sa = nullptr, *sb = nullptr, *q = nullptr;
+  char *p = nullptr, *r = nullptr, *q = nullptr;
+  char* sbuf[MAX_SBUF]{};      // ring of search-direction buffers (plane 0 pointers)
+  int nsbuf = 8;               // m: x is updated every m iterations (SPL_NSBUF)
   char *z = nullptr, *einv = nullptr;
   uint8_t *media = nullptr, *codes = nullptr;
   Scal* sc = nullptr;          // device
@@ -244,10 +248,14 @@ __global__ void k_finalize(Scal* sc, int par_last) {
   sc->converged = (!bad && rmax <= sc->tol * sc->bmax) ? 1 : 0;
 }
 
+// planes each phase-A CTA marches through.  Long chunks amortise the pipeline
+// prologue (2-3 extra planes of loads per chunk), short ones give more CTAs and a
+// smaller tail; ~2048 CTAs (4-5 waves at 3 CTAs/SM) measured best at 512^3
+// (profiles/r1_phaseA_zchunk.md).
 int phaseA_zchunk(const spl_ctx* c, int tiles_xy) {
   if (c->zchunk_override > 0) return c->zchunk_override;
   const int nz = c->g.nz;
-  const int target_blocks = c->sms * 8 * 4;
+  const int target_blocks = 2048;
   int gz = (target_blocks + tiles_xy - 1) / tiles_xy;
   if (gz < 1) gz = 1;
   int zc = (nz + gz - 1) / gz;
@@ -275,8 +283,14 @@ struct Impl {
     } else {
       const T cc = T(-(dt / c->d.h));
       const dim3 agrid((g.nx + 31) / 32, (g.ny + 7) / 8, g.nz < 65535 ? g.nz : 65535);
-      LAUNCH(c, k_advect<T>, agrid, dim3(32, 8), g, c->media, P(c->u), P(c->v), P(c->w), P(c->u2),
-             P(c->v2), P(c->w2), cc, c->sc);
+      // cells the hot kernel cannot prove safe go to a worklist kept in the PCG
+      // scratch field q (>= 4 B per cell, free during advection)
+      int* worklist = reinterpret_cast<int*>(c->q);
+      CU(cudaMemsetAsync(&c->sc->wl_count, 0, sizeof(unsigned), c->stream));
+      LAUNCH(c, k_advect<T>, agrid, dim3(32, 8), g, c->media, P(c->u), P(c->v), P(c->w),
+             P(c->u2), P(c->v2), P(c->w2), cc, worklist, c->sc);
+      LAUNCH(c, k_advect_rest<T>, grid, 256, g, P(c->u), P(c->v), P(c->w), P(c->u2),
+             P(c->v2), P(c->w2), cc, worklist, c->sc);
     }
     CU(cudaGetLastError());
     std::swap(c->u, c->u2);
@@ -317,25 +331,28 @@ struct Impl {
           c->ring_attr_set |= (1 << PC);
         }
         k_phaseA_ring<PC><<<gridA, blockA, sizeof(RingSmem), c->stream>>>(
-            g, c->codes, zr, sold, snew, P(c->q), reinterpret_cast<double*>(c->p), c->sc,
-            c->partials, par, zc);
+            g, c->codes, zr, sold, snew, P(c->q), c->sc, c->partials, par, zc);
         c->launches++;
         return;
       }
     }
     LAUNCH(c, (k_phaseA<T, VEC, PC>), gridA, blockA, g, c->codes, zr, sold, snew, P(c->q),
-           reinterpret_cast<double*>(c->p), c->sc, c->partials, par, zc);
+           c->sc, c->partials, par, zc);
   }
 
   template <int VEC, int PC>
   static int pcg(spl_ctx* c) {
     const Geo& g = c->g;
     const size_t fb = field_bytes(c, sizeof(T));
-    // x = 0, s = 0 (with halos), q = 0
+    // x = 0, s_0 = 0 (with halos), q = 0.  Only direction buffer 0 is read before
+    // it is written (as s_0 with beta = 0); the halo planes of every buffer are
+    // zero from allocation and only ever receive a neighbour slab's planes.
+    const int m = c->nsbuf;
     CU(cudaMemsetAsync(c->alloc[6], 0, field_bytes(c, 8), c->stream));   // p (fp64)
-    CU(cudaMemsetAsync(c->alloc[8], 0, fb, c->stream));   // sa
-    CU(cudaMemsetAsync(c->alloc[9], 0, fb, c->stream));   // sb
+    CU(cudaMemsetAsync(c->sbuf[0] - (size_t)g.hz * g.plane * sizeof(T), 0, fb, c->stream));
     CU(cudaMemsetAsync(c->alloc[10], 0, fb, c->stream));  // q
+    SBufs bufs;
+    for (int i = 0; i < MAX_SBUF; ++i) bufs.p[i] = c->sbuf[i < m ? i : 0];
     // scalars
     Scal* h = c->hsc;
     const unsigned long long keep_nf = 0;
@@ -359,16 +376,15 @@ struct Impl {
 
     // rho_0 = r.z, max|b|  (phase B with alpha = 0)
     LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
-           c->sc, c->partials, 0, 1);
+           c->sc, c->partials, 0, 1, m);
     int rc = gather_slots(c, &c->sc->gBM[0][0][0], 2);
     if (rc) return rc;
     LAUNCH(c, k_set_bmax, 1, 1, c->sc);
     CU(cudaGetLastError());
 
     const int limit = c->fixed_iters > 0 ? c->fixed_iters : c->d.max_iters;
-    char* sold = c->sa;
-    char* snew = c->sb;
     int it = 0;
+    int nflush = 0;
     bool done = false;
     const int poll = 16;
     while (it < limit && !done) {
@@ -376,6 +392,8 @@ struct Impl {
       for (; it < stop;) {
         ++it;
         const int par = it & 1;
+        char* sold = c->sbuf[(it - 1) % m];   // s_{it-1}
+        char* snew = c->sbuf[it % m];         // s_it
         if (c->d.world > 1) {
           LAUNCH(c, (k_dir_boundary<T, PC>), grid_for(c, 2 * g.plane), 256, g, c->codes, zr,
                  P(sold), P(snew), c->sc, par);
@@ -388,10 +406,17 @@ struct Impl {
         if ((rc = gather_slots(c, c->sc->gA, 1))) return rc;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 2], c->stream));
         LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
-               c->sc, c->partials, par, 0);
+               c->sc, c->partials, par, 0, m);
         if (prof) CU(cudaEventRecord(c->pev[3 * c->profile_iters + (it - 1)], c->stream));
         if ((rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
-        std::swap(sold, snew);
+        if (it % m == 0) {   // every buffer holds an unflushed direction: x += sum alpha s
+          const bool pf = c->profile_iters > 0 && nflush < 64;
+          if (pf) CU(cudaEventRecord(c->xev[2 * nflush], c->stream));
+          LAUNCH(c, (k_xflush<T, VEC>), gridB, 256, g, reinterpret_cast<double*>(c->p), bufs,
+                 c->sc, m);
+          if (pf) CU(cudaEventRecord(c->xev[2 * nflush + 1], c->stream));
+          ++nflush;
+        }
       }
       CU(cudaGetLastError());
       if (c->fixed_iters > 0 && it < limit) continue;
@@ -400,9 +425,10 @@ struct Impl {
       CU(cudaStreamSynchronize(c->stream));
       done = c->hsc->done != 0;
     }
-    // the last alpha_K s_K is still pending (phase A adds the previous term)
-    LAUNCH(c, (k_xflush<T, VEC>), gridB, 256, g, reinterpret_cast<double*>(c->p), P(c->sa),
-           P(c->sb), c->sc);
+    // terms of the last (K mod m) iterations are still pending
+    c->profile_flushes = nflush < 64 ? nflush : 64;
+    LAUNCH(c, (k_xflush<T, VEC>), gridB, 256, g, reinterpret_cast<double*>(c->p), bufs, c->sc,
+           m);
     LAUNCH(c, k_finalize, 1, 1, c->sc, it & 1);
     CU(cudaGetLastError());
     return SPL_OK;
@@ -554,6 +580,8 @@ void spl_destroy(spl_ctx* c) {
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->tev)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->xev)
+    if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -563,6 +591,9 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   spl_desc& d = c->d;
   if (d.nx < 1 || d.ny < 1 || d.nz < 1)
     return fail(c, SPL_E_BADARG, "box %d x %d x %d is empty", d.nx, d.ny, d.nz);
+  if ((long long)d.nx * d.ny * ((long long)d.nz + 8) >= 2147483647LL)
+    return fail(c, SPL_E_BADARG, "box %d x %d x %d exceeds 2^31 cells per context: "
+                "cut it into z-slabs", d.nx, d.ny, d.nz);
   if (d.dtype != SPL_F32 && d.dtype != SPL_F64)
     return fail(c, SPL_E_BADARG, "dtype %d is neither SPL_F32 nor SPL_F64", d.dtype);
   if (!(d.h > 0.0) || !(d.rho > 0.0))
@@ -601,10 +632,19 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
   for (auto& e : c->tev) CU(cudaEventCreate(&e));
   int rc;
+  char* unused8 = nullptr;
+  char* unused9 = nullptr;
   char** fields[] = {&c->u, &c->v, &c->w, &c->u2, &c->v2, &c->w2, &c->p, &c->r,
-                     &c->sa, &c->sb, &c->q};
-  for (int i = 0; i < 11; ++i)   // p (slot 6) is always fp64
+                     &unused8, &unused9, &c->q};
+  for (int i = 0; i < 11; ++i) {   // p (slot 6) is always fp64
+    if (i == 8 || i == 9) continue;
     if ((rc = alloc_field(c, i, i == 6 ? 8 : c->esz, fields[i], 0))) return rc;
+  }
+  if (const char* e = getenv("SPL_NSBUF")) c->nsbuf = atoi(e);
+  if (c->nsbuf < 2) c->nsbuf = 2;
+  if (c->nsbuf > MAX_SBUF) c->nsbuf = MAX_SBUF;
+  for (int i = 0; i < c->nsbuf; ++i)
+    if ((rc = alloc_field(c, 16 + i, c->esz, &c->sbuf[i], 0))) return rc;
   if (d.precond == SPL_PC_RBIC0) {
     if ((rc = alloc_field(c, 11, c->esz, &c->z, 0))) return rc;
     if ((rc = alloc_field(c, 12, c->esz, &c->einv, 0))) return rc;
@@ -910,8 +950,8 @@ int spl_timer_stop(spl_ctx* c, float* ms) {
   return SPL_OK;
 }
 
-int spl_profile_pcg(spl_ctx* c, double dt, int iters, float* ms_a, float* ms_b) {
-  if (!c || !ms_a || !ms_b) return SPL_E_BADARG;
+int spl_profile_pcg(spl_ctx* c, double dt, int iters, float* ms_a, float* ms_b, float* ms_x) {
+  if (!c || !ms_a || !ms_b || !ms_x) return SPL_E_BADARG;
   if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_profile_pcg before spl_upload");
   if (iters < 1 || iters > 256) return fail(c, SPL_E_BADARG, "iters must be in [1, 256]");
   if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
@@ -921,6 +961,9 @@ int spl_profile_pcg(spl_ctx* c, double dt, int iters, float* ms_a, float* ms_b) 
   const int n_ev = 4 * iters;
   cudaEvent_t* evs = new cudaEvent_t[n_ev];
   for (int i = 0; i < n_ev; ++i) CU(cudaEventCreate(&evs[i]));
+  for (auto& e : c->xev)
+    if (!e) CU(cudaEventCreate(&e));
+  c->profile_flushes = 0;
   c->pev = evs;
   c->profile_iters = iters;
   const int keep_fixed = c->fixed_iters;
@@ -943,6 +986,13 @@ int spl_profile_pcg(spl_ctx* c, double dt, int iters, float* ms_a, float* ms_b) 
     }
     *ms_a = (float)(a / iters);
     *ms_b = (float)(b / iters);
+    double xs = 0.0;
+    for (int i = 0; i < c->profile_flushes; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, c->xev[2 * i], c->xev[2 * i + 1]);
+      xs += t;
+    }
+    *ms_x = c->profile_flushes ? (float)(xs / c->profile_flushes) : 0.f;
   }
   for (int i = 0; i < n_ev; ++i) cudaEventDestroy(evs[i]);
   delete[] evs;

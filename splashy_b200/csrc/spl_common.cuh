@@ -23,6 +23,7 @@ constexpr int B_XM = 1, B_XP = 2, B_YM = 4, B_YP = 8, B_ZM = 16, B_ZP = 32,
 constexpr int MAXW = 16;       // max ranks (z-slabs)
 constexpr int TILE_Y = 8;      // rows per CTA in the marching stencil kernels
 constexpr int MAX_PARTIALS = 1 << 16;
+constexpr int MAX_SBUF = 8;    // ring of search-direction buffers (deferred x update)
 
 struct Geo {
   int nx, ny, nz;      // local box
@@ -46,8 +47,11 @@ struct Scal {
   unsigned long long nonfinite;   // summed over ranks on the host
   unsigned long long escapes;     // advection departures outside halo
   int world, rank;
+  double alpha_hist[MAX_SBUF];    // step length of iteration it at [it % m]
   int done, iters, count, breakdown, converged;
-  unsigned ticketA, ticketB, ticketC;
+  int flushed;                    // iterations whose alpha s term is already in x
+  unsigned ticketA, ticketB, ticketC, ticketX;
+  unsigned wl_count;              // advection worklist length
 };
 
 template <typename T, int N>

@@ -4,15 +4,16 @@
 // A is never formed; one PCG iteration is two kernels separated by
 // the two global reductions CG needs:
 //
-//   phase A(it): s' = z + beta s ; q = A s' ; partial s'.q ;
-//                x += alpha_{it-1} s            (the previous direction, which
-//                                                this kernel reads anyway)
-//   phase B(it): r -= alpha q ; partial r.z, max|r|
+//   phase A(it): s' = z + beta s ; q = A s' ; partial s'.q      17 B/cell (fp32)
+//   phase B(it): r -= alpha q ; partial r.z, max|r|            13 B/cell
+//   x flush    : x += sum_i alpha_i s_i   every m iterations   (4m + 16)/m B/cell
 //
-// The pressure accumulator x is always fp64: with fp32 storage its rounding
-// (eps |p|) is what limits the divergence-free residual on 256^3+ grids.
-// fp32 fields: A = r4 + s4 + code1 + x8 -> s'4 + q4 + x8 = 33 B/cell,
-//              B = r4 + q4 + code1 -> r4 = 13 B/cell.
+// The search directions of the last m iterations stay in a ring of m buffers
+// (phase A writes s' into the next one instead of ping-ponging two), so the
+// pressure accumulator x is touched once per m iterations instead of every
+// iteration: m = 4 -> 8 B/cell/iteration instead of 20.  x is always fp64:
+// with fp32 storage its rounding (eps |p|) is what limits the divergence-free
+// residual on 256^3+ grids.
 //
 // HBM-bound; no tensor cores (no dense contraction on this path).
 #pragma once
@@ -75,10 +76,10 @@ __device__ __forceinline__ T lap_cell(unsigned code, T s0, T xm, T xp, T ym, T y
 // in registers.  +-x neighbours come from warp shuffles, +-y neighbours from a
 // triple-buffered shared-memory tile (one barrier per plane); only the two
 // CTA-edge rows and the CTA-edge lanes recompute a halo value from global
-// memory.  Software pipeline: the raw operands (r, s, codes, x) of plane c+2
-// are requested at the top of iteration c and first touched at the top of
-// iteration c+1, so a whole plane of loads per thread is always in flight.
-// Every array is pulled from HBM once.
+// memory.  Software pipeline: the raw operands (r, s, codes) of plane c+2 are
+// requested at the top of iteration c, after those of plane c+1 were consumed,
+// so a plane of loads per thread is in flight across the barrier and the
+// stencil.  Every array is pulled from HBM once.
 template <typename T, int VEC>
 struct RawV {
   VecT<T, VEC> a, old;
@@ -143,56 +144,54 @@ struct DirLoader {
   }
 };
 
+// beta, stop decision: shared by both phase-A kernels (thread 0 of every CTA)
+__device__ __forceinline__ void phaseA_scalars(Scal* sc, int par, int* stop_out, double* beta_out) {
+  int stop = sc->done;
+  double beta = 0.0;
+  if (!stop) {
+    const double rho1 = rho_of(sc, par ^ 1);   // rho_{it-1}
+    const double rho2 = rho_of(sc, par);       // rho_{it-2}
+    const double rmax = rmax_of(sc, par ^ 1);  // max|r| after iteration it-1
+    const double bmax = sc->bmax;
+    const bool bad = !(rmax == rmax);
+    if (bad || rmax <= sc->tol * bmax || rho1 == 0.0) {
+      stop = 1;
+      if (linear_block() == 0) {
+        sc->iters = sc->count;
+        sc->rmax = rmax;
+        sc->converged = bad ? 0 : 1;
+        sc->breakdown = bad ? 1 : 0;
+        __threadfence();
+        sc->done = 1;
+      }
+    } else {
+      beta = rho1 / rho2;     // rho2 = +inf before the first iteration
+    }
+  }
+  *stop_out = stop;
+  *beta_out = beta;
+}
+
 #ifndef SPL_PHASEA_MINB
-#define SPL_PHASEA_MINB 3     // resident CTAs per SM for fp32 (fp64: one less)
+#define SPL_PHASEA_MINB 4     // resident CTAs per SM for fp32 (fp64: half)
 #endif
 template <typename T, int VEC, int PC>
-__global__ void __launch_bounds__(32 * TILE_Y, (sizeof(T) == 8) ? SPL_PHASEA_MINB - 1 : SPL_PHASEA_MINB)
+__global__ void __launch_bounds__(32 * TILE_Y, (sizeof(T) == 8) ? SPL_PHASEA_MINB / 2 : SPL_PHASEA_MINB)
 k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
          const T* __restrict__ sold, T* __restrict__ snew, T* __restrict__ q,
-         double* __restrict__ x, Scal* __restrict__ sc, double* __restrict__ partials,
-         int par, int zchunk) {
+         Scal* __restrict__ sc, double* __restrict__ partials, int par, int zchunk) {
   __shared__ double red[32];
-  __shared__ double s_beta, s_alpha;
+  __shared__ double s_beta;
   __shared__ int s_stop;
   __shared__ T lut[8];
   __shared__ VecT<T, VEC> tile[3][TILE_Y + 2][32];
   const int tid = threadIdx.x + threadIdx.y * 32;
   fill_inv_lut<T>(lut);
-  if (tid == 0) {
-    int stop = sc->done;
-    double beta = 0.0, alpha_prev = 0.0;
-    if (!stop) {
-      const double rho1 = rho_of(sc, par ^ 1);   // rho_{it-1}
-      const double rho2 = rho_of(sc, par);       // rho_{it-2}
-      const double rmax = rmax_of(sc, par ^ 1);  // max|r| after iteration it-1
-      const double bmax = sc->bmax;
-      const bool bad = !(rmax == rmax);
-      if (bad || rmax <= sc->tol * bmax || rho1 == 0.0) {
-        stop = 1;
-        if (linear_block() == 0) {
-          sc->iters = sc->count;
-          sc->rmax = rmax;
-          sc->converged = bad ? 0 : 1;
-          sc->breakdown = bad ? 1 : 0;
-          __threadfence();
-          sc->done = 1;
-        }
-      } else {
-        beta = rho1 / rho2;     // rho2 = +inf before the first iteration
-        // step length of the previous iteration (what phase B(it-1) used)
-        if (sc->count > 0) alpha_prev = rho2 / sum_slots(sc->gA, sc->world);
-      }
-    }
-    s_stop = stop;
-    s_beta = beta;
-    s_alpha = alpha_prev;
-  }
+  if (tid == 0) phaseA_scalars(sc, par, &s_stop, &s_beta);
   __syncthreads();
   if (s_stop) return;
 
   const DirLoader<T, VEC, PC> dl{codes, zr, sold, snew, lut, g.nz, T(s_beta)};
-  const double alpha_prev = s_alpha;
   const int lane = threadIdx.x, ty = threadIdx.y;
   const int i0 = (blockIdx.x * 32 + lane) * VEC;
   const int j = blockIdx.y * TILE_Y + ty;
@@ -201,9 +200,10 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
   const int ke = min(kb + zchunk, g.nz);
   const long long row = g.nx, plane = g.plane;
   // CTA-edge rows recompute the neighbouring row, CTA-edge lanes the x
-  // neighbour owned by the adjacent CTA (memory is always valid thanks to the z
-  // halo planes; values outside the box are masked by the code bits)
-  const bool has_hrow = active && (ty == 0 || ty == TILE_Y - 1);
+  // neighbour owned by the adjacent CTA.  Rows / columns outside the box must
+  // read as 0 (the Laplacian is unmasked, see lap_cell).
+  const int hrow_j = (ty == 0) ? j - 1 : j + 1;
+  const bool hrow_ok = active && (ty == 0 || ty == TILE_Y - 1) && hrow_j >= 0 && hrow_j < g.ny;
   const long long hoff = (ty == 0) ? -row : row;
   const int hslot = (ty == 0) ? 0 : TILE_Y + 1;
   const bool has_e = active && ((lane == 0 && i0 > 0) || (lane == 31 && i0 + VEC < g.nx));
@@ -211,34 +211,28 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
 
   VecT<T, VEC> zero;
   VecT<uint8_t, VEC> czero;
-  VecT<double, VEC> dzero;
 #pragma unroll
-  for (int e = 0; e < VEC; ++e) { zero.v[e] = T(0); czero.v[e] = 0; dzero.v[e] = 0.0; }
+  for (int e = 0; e < VEC; ++e) { zero.v[e] = T(0); czero.v[e] = 0; }
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    if (!active) tile[b][ty + 1][lane] = zero;                            // own row
+    if (ty == 0 && !hrow_ok) tile[b][0][lane] = zero;                     // row j-1
+    if (ty == TILE_Y - 1 && !hrow_ok) tile[b][TILE_Y + 1][lane] = zero;   // row j+1
+  }
 
   double acc = 0.0;
   long long idx = ((long long)kb * g.ny + j) * row + i0;
-  VecT<T, VEC> sm = zero, scur = zero, sp = zero, oldc = zero;
+  VecT<T, VEC> sm = zero, scur = zero, sp = zero;
   VecT<uint8_t, VEC> codec = czero;
-  VecT<double, VEC> xc = dzero, xn = dzero;
   RawV<T, VEC> raw{zero, zero, czero}, hraw{zero, zero, czero};
   RawS<T> eraw{T(0), T(0), 0u};
   T leftc = T(0), rightc = T(0);
 
-  // rows outside the box must read as 0 (the Laplacian is unmasked)
-  const int hrow_j = (ty == 0) ? j - 1 : j + 1;
-  const bool hrow_ok = has_hrow && hrow_j >= 0 && hrow_j < g.ny;
-#pragma unroll
-  for (int b = 0; b < 3; ++b) {
-    if (!active) tile[b][ty + 1][lane] = zero;                       // own row
-    if (ty == 0 && !hrow_ok) tile[b][0][lane] = zero;                // row j-1
-    if (ty == TILE_Y - 1 && !hrow_ok) tile[b][TILE_Y + 1][lane] = zero;   // row j+1
-  }
   // ---- prologue: planes kb-1 and kb combined, plane kb+1 requested ----------
   if (active) {
     sm = dl.combine(dl.load(idx - plane, kb - 1), kb - 1);
     const RawV<T, VEC> r0 = dl.load(idx, kb);
     scur = dl.combine(r0, kb);
-    oldc = r0.old;
     codec = r0.code;
     tile[kb % 3][ty + 1][lane] = scur;
     if (hrow_ok) tile[kb % 3][hslot][lane] = dl.combine(dl.load(idx + hoff, kb), kb);
@@ -246,24 +240,20 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
       const T e = dl.combine1(dl.load1(idx + eoff, kb), kb);
       if (lane == 0) leftc = e; else rightc = e;
     }
-    xc = vload<double, VEC>(x, idx);
     raw = dl.load(idx + plane, kb + 1);
     if (kb + 1 < ke) {
       if (hrow_ok) hraw = dl.load(idx + plane + hoff, kb + 1);
       if (has_e) eraw = dl.load1(idx + plane + eoff, kb + 1);
-      xn = vload<double, VEC>(x, idx + plane);
     }
   }
 
   for (int c = kb; c < ke; ++c, idx += plane) {
     const int tb = c % 3, tn = (c + 1) % 3;
-    VecT<T, VEC> oldn = zero;
     VecT<uint8_t, VEC> coden = czero;
     T leftn = T(0), rightn = T(0);
     if (active) {
       // plane c+1: operands were requested one iteration ago
       sp = dl.combine(raw, c + 1);
-      oldn = raw.old;
       coden = raw.code;
       if (c + 1 < ke) {
         tile[tn][ty + 1][lane] = sp;
@@ -302,19 +292,12 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
       acc += (double)part;   // VEC products in working precision, accumulated in fp64
       vstore<T, VEC>(q, idx, qv);
       vstore<T, VEC>(snew, idx, scur);
-      // x += alpha_{it-1} * s_{it-1}  (fp64 accumulator, requested >= 1 plane ago)
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) xc.v[e] += alpha_prev * (double)oldc.v[e];
-      vstore<double, VEC>(x, idx, xc);
     }
     sm = scur;
     scur = sp;
-    oldc = oldn;
     codec = coden;
     leftc = leftn;
     rightc = rightn;
-    xc = xn;
-    if (active && c + 2 < ke) xn = vload<double, VEC>(x, idx + 2 * plane);
   }
 
   const double bs = block_sum(acc, red);
@@ -329,14 +312,17 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
 }
 
 // ---- phase A, cp.async ring variant (fp32, VEC = 4) ---------------------------
-// Same arithmetic as k_phaseA.  B200 needs ~100 KB of loads in flight per SM to
-// saturate HBM3e; a register software pipeline cannot hold that (every byte in
-// flight pins a register).  Here each thread streams the raw operands of the
-// next RING_D - 1 planes (r, s, codes, fp64 x; plus the CTA-edge rows / lanes)
-// into its own slots of a shared-memory ring with cp.async (LDGSTS) and only
-// touches them after cp.async.wait_group, so registers hold just the three
-// combined planes.  The slots are thread-private: no extra barrier is needed.
-constexpr int RING_D = 4;
+// Same arithmetic as k_phaseA.  B200 wants on the order of 100 KB of loads in
+// flight per SM to saturate HBM3e; every byte a register pipeline keeps in
+// flight pins a register.  Here each thread streams the raw operands of the
+// next RING_D - 1 planes (r, s, codes; plus the CTA-edge rows / lanes) into its
+// own slots of a shared-memory ring with cp.async (LDGSTS) and only touches
+// them after cp.async.wait_group, so registers hold just the three combined
+// planes.  The slots are thread-private: no extra barrier is needed.
+#ifndef SPL_RING_D
+#define SPL_RING_D 5
+#endif
+constexpr int RING_D = SPL_RING_D;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -354,19 +340,9 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// TMA-engine bulk prefetch into L2 (UBLKPF): one lane moves a whole tile row
-// from HBM towards the SM without holding registers or shared memory.
-__device__ __forceinline__ void prefetch_l2(const void* gmem, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
-}
-#ifndef SPL_L2_AHEAD
-#define SPL_L2_AHEAD 3     // planes between the L2 prefetch and the cp.async request
-#endif
-
 struct alignas(16) RingStage {
   float4 a[256];          // z or r of the thread's 4 cells
   float4 old[256];        // previous search direction
-  float4 x[2][256];       // fp64 pressure accumulator (4 doubles = 2 x 16 B)
   float4 ha[64];          // CTA-edge rows (warp 0: row j-1, warp 7: row j+8)
   float4 hold[64];
   unsigned code[256];
@@ -380,53 +356,27 @@ struct RingSmem {
   float4 tile[3][TILE_Y + 2][32];
   double red[32];
   float lut[8];
-  double beta, alpha;
+  double beta;
   int stop;
 };
 
+#ifndef SPL_RING_MINB
+#define SPL_RING_MINB 3
+#endif
 template <int PC>
-__global__ void __launch_bounds__(32 * TILE_Y, 2)
+__global__ void __launch_bounds__(32 * TILE_Y, SPL_RING_MINB)
 k_phaseA_ring(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ zr,
               const float* __restrict__ sold, float* __restrict__ snew, float* __restrict__ q,
-              double* __restrict__ x, Scal* __restrict__ sc, double* __restrict__ partials,
-              int par, int zchunk) {
+              Scal* __restrict__ sc, double* __restrict__ partials, int par, int zchunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RingSmem& sm_ = *reinterpret_cast<RingSmem*>(smem_raw);
   const int tid = threadIdx.x + threadIdx.y * 32;
   fill_inv_lut<float>(sm_.lut);
-  if (tid == 0) {
-    int stop = sc->done;
-    double beta = 0.0, alpha_prev = 0.0;
-    if (!stop) {
-      const double rho1 = rho_of(sc, par ^ 1);
-      const double rho2 = rho_of(sc, par);
-      const double rmax = rmax_of(sc, par ^ 1);
-      const double bmax = sc->bmax;
-      const bool bad = !(rmax == rmax);
-      if (bad || rmax <= sc->tol * bmax || rho1 == 0.0) {
-        stop = 1;
-        if (linear_block() == 0) {
-          sc->iters = sc->count;
-          sc->rmax = rmax;
-          sc->converged = bad ? 0 : 1;
-          sc->breakdown = bad ? 1 : 0;
-          __threadfence();
-          sc->done = 1;
-        }
-      } else {
-        beta = rho1 / rho2;
-        if (sc->count > 0) alpha_prev = rho2 / sum_slots(sc->gA, sc->world);
-      }
-    }
-    sm_.stop = stop;
-    sm_.beta = beta;
-    sm_.alpha = alpha_prev;
-  }
+  if (tid == 0) phaseA_scalars(sc, par, &sm_.stop, &sm_.beta);
   __syncthreads();
   if (sm_.stop) return;
 
   const float beta = (float)sm_.beta;
-  const double alpha_prev = sm_.alpha;
   const float* lut = sm_.lut;
   const int lane = threadIdx.x, ty = threadIdx.y;
   const int i0 = (blockIdx.x * 32 + lane) * 4;
@@ -456,33 +406,31 @@ k_phaseA_ring(Geo g, const uint8_t* __restrict__ codes, const float* __restrict_
   const int eidx = ty * 2 + ((lane == 0) ? 0 : 1);
   const long long idx0 = ((long long)kb * g.ny + j) * row + i0;   // plane kb
 
-  // request every operand of plane p into ring slot p % RING_D
-  auto request = [&](int p) {
+  // request every operand of plane p into ring slot `slot`; `off` = element
+  // offset of the thread's cells on plane p (running values: no div / mod / 64-bit
+  // multiplies in the loop)
+  auto request = [&](int p, int slot, long long off) {
     if (active && p <= ke) {
-      RingStage& st = sm_.st[p % RING_D];
-      const long long idx = idx0 + (long long)(p - kb) * plane;
+      RingStage& st = sm_.st[slot];
       const bool remote = (p < 0) || (p >= nz);
       if (remote) {
-        cp_async16(&st.a[tid], snew + idx);          // halo of s' already holds the new direction
+        cp_async16(&st.a[tid], snew + off);          // halo of s' already holds the new direction
       } else {
-        cp_async16(&st.a[tid], zr + idx);
-        cp_async16(&st.old[tid], sold + idx);
-        cp_async4(&st.code[tid], codes + idx);
+        cp_async16(&st.a[tid], zr + off);
+        cp_async16(&st.old[tid], sold + off);
+        cp_async4(&st.code[tid], codes + off);
       }
       if (p < ke) {                                    // centre planes only
-        cp_async16(&st.x[0][tid], x + idx);
-        cp_async16(&st.x[1][tid], x + idx + 2);
         if (has_hrow) {
-          cp_async16(&st.ha[hidx], zr + idx + hoff);
-          cp_async16(&st.hold[hidx], sold + idx + hoff);
-          cp_async4(&st.hcode[hidx], codes + idx + hoff);
+          cp_async16(&st.ha[hidx], zr + off + hoff);
+          cp_async16(&st.hold[hidx], sold + off + hoff);
+          cp_async4(&st.hcode[hidx], codes + off + hoff);
         }
         if (has_e) {
-          cp_async4(&st.ea[eidx], zr + idx + eoff);
-          cp_async4(&st.eold[eidx], sold + idx + eoff);
+          cp_async4(&st.ea[eidx], zr + off + eoff);
+          cp_async4(&st.eold[eidx], sold + off + eoff);
           // 4-byte aligned word that contains the neighbour's code byte
-          const long long cidx = idx + eoff;
-          cp_async4(&st.ecode[eidx], codes + (cidx & ~3LL));
+          cp_async4(&st.ecode[eidx], codes + ((off + eoff) & ~3LL));
         }
       }
     }
@@ -492,111 +440,100 @@ k_phaseA_ring(Geo g, const uint8_t* __restrict__ codes, const float* __restrict_
     const float zz = (PC == PC_JACOBI) ? a * lut[lut_index(code)] : a;
     return zz + beta * o;
   };
-  // combined plane p (own cells) from its ring slot; also the tile halo row and
-  // the CTA-edge x neighbour when p is a centre plane
-  auto combine_own = [&](int p) {
-    const RingStage& st = sm_.st[p % RING_D];
+  auto dir4 = [&](float4 a, float4 o, unsigned c) {
+    float4 r;
+    r.x = dirf(a.x, o.x, c & 0xffu);
+    r.y = dirf(a.y, o.y, (c >> 8) & 0xffu);
+    r.z = dirf(a.z, o.z, (c >> 16) & 0xffu);
+    r.w = dirf(a.w, o.w, c >> 24);
+    return r;
+  };
+  // the neighbour's code byte inside the aligned word: lane 0 reads element
+  // i0 - 1 (byte 3 of the previous word), lane 31 element i0 + 4 (byte 0)
+  const int eshift = (lane == 0) ? 24 : 0;
+  auto combine_own = [&](int p, int slot, unsigned& code_out) {
+    const RingStage& st = sm_.st[slot];
     const float4 a = st.a[tid];
+    code_out = 0u;
     if (p < 0 || p >= nz) return a;
-    const float4 o = st.old[tid];
-    const unsigned c = st.code[tid];
-    float4 r;
-    r.x = dirf(a.x, o.x, c & 0xffu);
-    r.y = dirf(a.y, o.y, (c >> 8) & 0xffu);
-    r.z = dirf(a.z, o.z, (c >> 16) & 0xffu);
-    r.w = dirf(a.w, o.w, c >> 24);
-    return r;
+    code_out = st.code[tid];
+    return dir4(a, st.old[tid], code_out);
   };
-  auto combine_hrow = [&](int p) {
-    const RingStage& st = sm_.st[p % RING_D];
-    const float4 a = st.ha[hidx];
-    const float4 o = st.hold[hidx];
-    const unsigned c = st.hcode[hidx];
-    float4 r;
-    r.x = dirf(a.x, o.x, c & 0xffu);
-    r.y = dirf(a.y, o.y, (c >> 8) & 0xffu);
-    r.z = dirf(a.z, o.z, (c >> 16) & 0xffu);
-    r.w = dirf(a.w, o.w, c >> 24);
-    return r;
+  auto combine_hrow = [&](int slot) {
+    const RingStage& st = sm_.st[slot];
+    return dir4(st.ha[hidx], st.hold[hidx], st.hcode[hidx]);
   };
-  auto combine_edge = [&](int p) {
-    const RingStage& st = sm_.st[p % RING_D];
-    const long long cidx = idx0 + (long long)(p - kb) * plane + eoff;
-    const unsigned c = (st.ecode[eidx] >> (8 * (int)(cidx & 3LL))) & 0xffu;
-    return dirf(st.ea[eidx], st.eold[eidx], c);
+  auto combine_edge = [&](int slot) {
+    const RingStage& st = sm_.st[slot];
+    return dirf(st.ea[eidx], st.eold[eidx], (st.ecode[eidx] >> eshift) & 0xffu);
   };
+  auto next_slot = [](int s) { return (s + 1 == RING_D) ? 0 : s + 1; };
+  auto next_tile = [](int t) { return (t + 1 == 3) ? 0 : t + 1; };
 
   // ---- prologue ---------------------------------------------------------------
   float4 smv = make_float4(0.f, 0.f, 0.f, 0.f), scur = smv, sp = smv;
   float leftc = 0.f, rightc = 0.f;
-  for (int p = kb; p < kb + RING_D - 1; ++p) request(p);    // RING_D - 1 groups
+  long long roff = idx0;                                    // offset of the next requested plane
+  int rslot = 0;                                            // ring slot of the next requested plane
+  for (int p = kb; p < kb + RING_D - 1; ++p) {              // RING_D - 1 groups
+    request(p, rslot, roff);
+    roff += plane;
+    rslot = next_slot(rslot);
+  }
   if (active) {                                             // plane kb-1: registers
     const long long idm = idx0 - plane;
     if (kb - 1 < 0) {
       smv = *reinterpret_cast<const float4*>(snew + idm);
     } else {
-      const float4 a = *reinterpret_cast<const float4*>(zr + idm);
-      const float4 o = *reinterpret_cast<const float4*>(sold + idm);
-      const unsigned c = *reinterpret_cast<const unsigned*>(codes + idm);
-      smv.x = dirf(a.x, o.x, c & 0xffu);
-      smv.y = dirf(a.y, o.y, (c >> 8) & 0xffu);
-      smv.z = dirf(a.z, o.z, (c >> 16) & 0xffu);
-      smv.w = dirf(a.w, o.w, c >> 24);
+      smv = dir4(*reinterpret_cast<const float4*>(zr + idm),
+                 *reinterpret_cast<const float4*>(sold + idm),
+                 *reinterpret_cast<const unsigned*>(codes + idm));
     }
   }
   cp_async_wait<RING_D - 2>();                              // plane kb has landed
+  unsigned codec = 0;
+  int tcur = 0;                                             // tile buffer of plane c
   if (active) {
-    scur = combine_own(kb);
-    sm_.tile[kb % 3][ty + 1][lane] = scur;
-    if (has_hrow) sm_.tile[kb % 3][hslot][lane] = combine_hrow(kb);
+    scur = combine_own(kb, 0, codec);
+    sm_.tile[0][ty + 1][lane] = scur;
+    if (has_hrow) sm_.tile[0][hslot][lane] = combine_hrow(0);
     if (has_e) {
-      const float e = combine_edge(kb);
+      const float e = combine_edge(0);
       if (lane == 0) leftc = e; else rightc = e;
     }
   }
 
   double acc = 0.0;
   long long idx = idx0;
-  // HBM -> L2: lane 0 of every warp prefetches its tile row (r, s, codes, x) of
-  // the plane SPL_L2_AHEAD beyond the newest cp.async request
-  const bool pf_lane = (lane == 0) && (j < g.ny) && (blockIdx.x * 128 < g.nx);
-  const int pf_cells = min(128, g.nx - (int)blockIdx.x * 128);
-  auto prefetch_plane = [&](int p) {
-    if (SPL_L2_AHEAD > 0 && pf_lane && p < ke && p < nz) {
-      const long long id = idx0 + (long long)(p - kb) * plane;   // lane 0: tile row start
-      prefetch_l2(zr + id, pf_cells * 4);
-      prefetch_l2(sold + id, pf_cells * 4);
-      prefetch_l2(x + id, pf_cells * 8);
-      if ((pf_cells & 15) == 0) prefetch_l2(codes + id, pf_cells);
-    }
-  };
-  for (int p = kb + RING_D - 1; p < kb + RING_D - 1 + SPL_L2_AHEAD; ++p) prefetch_plane(p);
+  int nslot = 1;                                            // ring slot of plane c+1
   for (int c = kb; c < ke; ++c, idx += plane) {
-    prefetch_plane(c + RING_D - 1 + SPL_L2_AHEAD);
-    request(c + RING_D - 1);          // into the slot of plane c-1 (fully consumed)
-    cp_async_wait<RING_D - 2>();      // plane c+1 has landed
+    request(c + RING_D - 1, rslot, roff);   // into the slot of plane c-1 (fully consumed)
+    roff += plane;
+    rslot = next_slot(rslot);
+    cp_async_wait<RING_D - 2>();            // plane c+1 has landed
+    const int tnext = next_tile(tcur);
     float leftn = 0.f, rightn = 0.f;
+    unsigned coden = 0;
     if (active) {
-      sp = combine_own(c + 1);
+      sp = combine_own(c + 1, nslot, coden);
       if (c + 1 < ke) {
-        sm_.tile[(c + 1) % 3][ty + 1][lane] = sp;
-        if (has_hrow) sm_.tile[(c + 1) % 3][hslot][lane] = combine_hrow(c + 1);
+        sm_.tile[tnext][ty + 1][lane] = sp;
+        if (has_hrow) sm_.tile[tnext][hslot][lane] = combine_hrow(nslot);
         if (has_e) {
-          const float e = combine_edge(c + 1);
+          const float e = combine_edge(nslot);
           if (lane == 0) leftn = e; else rightn = e;
         }
       }
     }
-    __syncthreads();   // tile[c % 3] was completed before the previous barrier
+    nslot = next_slot(nslot);
+    __syncthreads();   // tile[tcur] (plane c) was completed before the previous barrier
     const float lsh = __shfl_up_sync(0xffffffffu, scur.w, 1);
     const float rsh = __shfl_down_sync(0xffffffffu, scur.x, 1);
     const float left = (lane != 0) ? lsh : leftc;
     const float right = (lane != 31) ? rsh : rightc;
     if (active) {
-      const RingStage& st = sm_.st[c % RING_D];
-      const float4 sym = sm_.tile[c % 3][ty][lane];
-      const float4 syp = sm_.tile[c % 3][ty + 2][lane];
-      const unsigned code4 = st.code[tid];
+      const float4 sym = sm_.tile[tcur][ty][lane];
+      const float4 syp = sm_.tile[tcur][ty + 2][lane];
       const float s[4] = {scur.x, scur.y, scur.z, scur.w};
       const float ym[4] = {sym.x, sym.y, sym.z, sym.w};
       const float yp[4] = {syp.x, syp.y, syp.z, syp.w};
@@ -608,29 +545,20 @@ k_phaseA_ring(Geo g, const uint8_t* __restrict__ codes, const float* __restrict_
       for (int e = 0; e < 4; ++e) {
         const float xm = (e > 0) ? s[e > 0 ? e - 1 : 0] : left;
         const float xp = (e < 3) ? s[e < 3 ? e + 1 : 0] : right;
-        qa[e] = lap_cell<float>((code4 >> (8 * e)) & 0xffu, s[e], xm, xp, ym[e], yp[e], zm[e],
+        qa[e] = lap_cell<float>((codec >> (8 * e)) & 0xffu, s[e], xm, xp, ym[e], yp[e], zm[e],
                                 zp[e]);
         part += s[e] * qa[e];
       }
       acc += (double)part;   // 4 products in fp32, accumulated in fp64
       *reinterpret_cast<float4*>(q + idx) = make_float4(qa[0], qa[1], qa[2], qa[3]);
       *reinterpret_cast<float4*>(snew + idx) = scur;
-      // x += alpha_{it-1} * s_{it-1}  (fp64 accumulator)
-      const float4 o = st.old[tid];
-      const float4 x01 = st.x[0][tid], x23 = st.x[1][tid];
-      double2 xa = *reinterpret_cast<const double2*>(&x01);
-      double2 xb = *reinterpret_cast<const double2*>(&x23);
-      xa.x += alpha_prev * (double)o.x;
-      xa.y += alpha_prev * (double)o.y;
-      xb.x += alpha_prev * (double)o.z;
-      xb.y += alpha_prev * (double)o.w;
-      *reinterpret_cast<double2*>(x + idx) = xa;
-      *reinterpret_cast<double2*>(x + idx + 2) = xb;
     }
     smv = scur;
     scur = sp;
+    codec = coden;
     leftc = leftn;
     rightc = rightn;
+    tcur = tnext;
   }
   cp_async_wait<0>();
 
@@ -677,7 +605,7 @@ template <typename T, int VEC, int PC>
 __global__ void __launch_bounds__(256)
 k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
          const T* __restrict__ q, const T* __restrict__ z, Scal* __restrict__ sc,
-         double* __restrict__ partials, int par, int init) {
+         double* __restrict__ partials, int par, int init, int nsbuf) {
   __shared__ double red[32];
   __shared__ double s_alpha;
   __shared__ T lut[8];
@@ -690,6 +618,9 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
       const double rho1 = rho_of(sc, par ^ 1);
       const double sq = sum_slots(sc->gA, sc->world);
       alpha = rho1 / sq;
+      // remembered for the deferred x update (iteration number = count + 1;
+      // count only moves after every CTA of this launch has passed this point)
+      if (blockIdx.x == 0) sc->alpha_hist[(sc->count + 1) % nsbuf] = alpha;
     }
     s_alpha = alpha;
   }
@@ -750,28 +681,54 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
   }
 }
 
-// ---- last pending x update ----------------------------------------------------
-// Phase A(it) adds alpha_{it-1} s_{it-1}; when the loop ends after K iterations
-// the last term alpha_K s_K is still pending.  s_K sits in buffer sb for odd K
-// and sa for even K (ping-pong), alpha_K = rho_{K-1} / (s_K . q_K).
+// ---- deferred pressure update ----------------------------------------------------
+// Iteration it leaves its search direction in ring buffer it % m and its step
+// length in alpha_hist[it % m]; this kernel adds every pending term
+//   x += sum_{it = flushed+1 .. count} alpha_it s_it        (fp64 accumulator)
+// and is launched after every m-th iteration and once after the loop, so a
+// buffer is always flushed before phase A overwrites it.
+struct SBufs {
+  const void* p[MAX_SBUF];
+};
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-k_xflush(Geo g, double* __restrict__ x, const T* __restrict__ sa, const T* __restrict__ sb,
-         const Scal* __restrict__ sc) {
-  const int K = sc->count;
-  if (K <= 0) return;
-  const T* __restrict__ s = (K & 1) ? sb : sa;
-  const double alpha = rho_of(sc, (K - 1) & 1) / sum_slots(sc->gA, sc->world);
-  if (!(fabs(alpha) <= 1.7976931348623157e308)) return;
-  const long long nq = g.ncell / VEC;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nq;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long idx = t * VEC;
-    const VecT<T, VEC> sv = vload<T, VEC>(s, idx);
-    VecT<double, VEC> xv = vload<double, VEC>(x, idx);
+k_xflush(Geo g, double* __restrict__ x, SBufs bufs, Scal* __restrict__ sc, int m) {
+  __shared__ double s_alpha[MAX_SBUF];
+  __shared__ const T* s_ptr[MAX_SBUF];
+  __shared__ int s_n;
+  const int lo = sc->flushed, hi = sc->count;
+  if (threadIdx.x == 0) {
+    int n = hi - lo;
+    if (n > m) n = m;
+    if (n < 0) n = 0;
+    for (int t = 0; t < n; ++t) {
+      const int it = lo + 1 + t;
+      const double a = sc->alpha_hist[it % m];
+      s_alpha[t] = (fabs(a) <= 1.7976931348623157e308) ? a : 0.0;
+      s_ptr[t] = static_cast<const T*>(bufs.p[it % m]);
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > 0) {
+    const long long nq = g.ncell / VEC;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nq;
+         t += (long long)gridDim.x * blockDim.x) {
+      const long long idx = t * VEC;
+      VecT<double, VEC> xv = vload<double, VEC>(x, idx);
+      for (int u = 0; u < n; ++u) {
+        const VecT<T, VEC> sv = vload<T, VEC>(s_ptr[u], idx);
+        const double a = s_alpha[u];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) xv.v[e] += alpha * (double)sv.v[e];
-    vstore<double, VEC>(x, idx, xv);
+        for (int e = 0; e < VEC; ++e) xv.v[e] += a * (double)sv.v[e];
+      }
+      vstore<double, VEC>(x, idx, xv);
+    }
+  }
+  if (last_block(&sc->ticketX, gridDim.x)) {
+    if (threadIdx.x == 0) sc->flushed = hi;
   }
 }
 

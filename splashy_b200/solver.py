@@ -205,11 +205,12 @@ class Solver:
         return float(ms.value)
 
     def profile_pcg(self, dt: float, iters: int = 32):
-        """(ms per phase-A launch, ms per phase-B launch), CUDA events."""
-        a, b = C.c_float(), C.c_float()
+        """(ms per phase-A launch, per phase-B launch, per x-flush launch),
+        measured with CUDA events on the library's stream."""
+        a, b, x = C.c_float(), C.c_float(), C.c_float()
         self._check(self._lib.spl_profile_pcg(self._ctx, dt, iters, C.byref(a),
-                                              C.byref(b)))
-        return float(a.value), float(b.value)
+                                              C.byref(b), C.byref(x)))
+        return float(a.value), float(b.value), float(x.value)
 
     def upload_ptrs(self, labels_ptr, u_ptr, v_ptr, w_ptr, p_ptr=None):
         """Raw host pointers (pinned buffers) -- no numpy conversion."""
