@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="splashy_b200", choices=["splashy_b200", "reference"])
     ap.add_argument("--n", type=int, default=512, help="x = y = per-GPU z extent")
     ap.add_argument("--pcg-iters", type=int, default=200)
+    ap.add_argument("--precond", default="jacobi", choices=["none", "jacobi", "rbic0"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tolerance-run", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the CPU sample box")
@@ -198,7 +199,7 @@ def run_cuda(args):
     cells_local = n ** 3
     cells = cells_local * world
 
-    s = Solver(n, n, n, dtype=np.float32, h=sc["h"], rho=sc["rho"], precond="jacobi",
+    s = Solver(n, n, n, dtype=np.float32, h=sc["h"], rho=sc["rho"], precond=args.precond,
                tol=1e-6, max_iters=20000, device=local, rank=rank, world=world,
                nz_global=nzg, z0=rank * n, nccl_id=nid)
     # pinned host buffers (the e2e leg copies from / to these every step)
@@ -329,7 +330,7 @@ def run_cuda(args):
             "config": {"workload": f"vortex_512: {n}x{n}x{n} cells per GPU (global {n}x{n}x{nzg}), "
                                    f"z-slabs, CFL 2, fp32 fields / fp64 dots",
                        "step": "advect + rhs + PCG + gradient + check",
-                       "pcg_iters": args.pcg_iters, "precond": "jacobi",
+                       "pcg_iters": args.pcg_iters, "precond": args.precond,
                        "l2": "inputs (3 x 512 MiB fields per GPU) exceed the 126 MB L2; no flush",
                        "parallelism": f"z-slab x{world}, NCCL halo + allgather"},
             "pcg_iters_per_s": iters_per_s,

@@ -323,7 +323,7 @@ struct Impl {
   static void launch_phaseA(spl_ctx* c, dim3 gridA, dim3 blockA, const T* zr, const T* sold,
                             T* snew, int par, int zc) {
     const Geo& g = c->g;
-    if constexpr (std::is_same<T, float>::value && VEC == 4 && PC != PC_RBIC0) {
+    if constexpr (std::is_same<T, float>::value && VEC == 4) {
       if (!c->no_ring) {
         if (!(c->ring_attr_set & (1 << PC))) {   // per context => per device
           cudaFuncSetAttribute(k_phaseA_ring<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -338,6 +338,26 @@ struct Impl {
     }
     LAUNCH(c, (k_phaseA<T, VEC, PC>), gridA, blockA, g, c->codes, zr, sold, snew, P(c->q),
            c->sc, c->partials, par, zc);
+  }
+
+  // red-black IC(0): z = M^-1 r in two half sweeps; the red sweep also leaves
+  // rho = r.z in slot `par`
+  static void precondition(spl_ctx* c, int par) {
+    const Geo& g = c->g;
+    const int grid = grid_for(c, g.ncell);
+    LAUNCH(c, (k_rb_sweep<T, 1>), grid, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc,
+           c->partials, par);
+    LAUNCH(c, (k_rb_sweep<T, 0>), grid, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc,
+           c->partials, par);
+  }
+
+  static int build_rbic0(spl_ctx* c) {
+    const Geo& g = c->g;
+    const int grid = grid_for(c, g.ncell);
+    LAUNCH(c, k_rb_contrib<T>, grid, 256, g, c->codes, c->media, P(c->z), c->d.tau);
+    LAUNCH(c, k_rb_einv<T>, grid, 256, g, c->codes, P(c->z), P(c->einv), 0.25);
+    CU(cudaGetLastError());
+    return SPL_OK;
   }
 
   template <int VEC, int PC>
@@ -377,6 +397,7 @@ struct Impl {
     // rho_0 = r.z, max|b|  (phase B with alpha = 0)
     LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
            c->sc, c->partials, 0, 1, m);
+    if (PC == PC_RBIC0) precondition(c, 0);
     int rc = gather_slots(c, &c->sc->gBM[0][0][0], 2);
     if (rc) return rc;
     LAUNCH(c, k_set_bmax, 1, 1, c->sc);
@@ -408,6 +429,7 @@ struct Impl {
         LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
                c->sc, c->partials, par, 0, m);
         if (prof) CU(cudaEventRecord(c->pev[3 * c->profile_iters + (it - 1)], c->stream));
+        if (PC == PC_RBIC0) precondition(c, par);   // z = M^-1 r, rho = r.z
         if ((rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
         if (it % m == 0) {   // every buffer holds an unflushed direction: x += sum alpha s
           const bool pf = c->profile_iters > 0 && nflush < 64;
@@ -439,9 +461,11 @@ struct Impl {
     if (c->vec == 4) {
       if (pc == SPL_PC_NONE) return pcg<4, PC_NONE>(c);
       if (pc == SPL_PC_JACOBI) return pcg<4, PC_JACOBI>(c);
+      if (pc == SPL_PC_RBIC0) return pcg<4, PC_RBIC0>(c);
     } else {
       if (pc == SPL_PC_NONE) return pcg<1, PC_NONE>(c);
       if (pc == SPL_PC_JACOBI) return pcg<1, PC_JACOBI>(c);
+      if (pc == SPL_PC_RBIC0) return pcg<1, PC_RBIC0>(c);
     }
     return fail(c, SPL_E_BADARG, "preconditioner %d is not available", pc);
   }
@@ -717,6 +741,10 @@ int spl_upload(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
   if (rc) return rc;
   LAUNCH(c, k_codes, grid_for(c, g.ncell), 256, g, c->media, c->codes);
   CU(cudaGetLastError());
+  if (c->d.precond == SPL_PC_RBIC0) {
+    rc = DISPATCH(c, Impl<float>::build_rbic0(c), Impl<double>::build_rbic0(c));
+    if (rc) return rc;
+  }
   CU(cudaStreamSynchronize(c->stream));
   c->uploaded = true;
   c->have_rhs = false;

@@ -681,6 +681,137 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
   }
 }
 
+// ---- red-black incomplete Cholesky preconditioner (SPL_PC_RBIC0) ------------------
+// Substitution for the reference's exact solve (Pressure.fs:69): natural-order
+// IC(0)/MIC(0) is sequential, so the factorisation is taken in red-black order
+// (red = (i+j+k) even first): M = (E + L) E^-1 (E + L^T) with
+//   E_red   = N_i,
+//   E_black = N_i - sum_{red Fluid nbr j} (1 + tau (nfl_j - 1)) / N_j   (safety 0.25 N_i)
+// (oracle/dense_ref.py rbic0_diag / apply_rbic0).  z = M^-1 r is two half sweeps:
+//   black: z_B = (r_B + sum_{red nbr} r_n einv_n) einv_B
+//   red  : z_R = (r_R + sum_{black nbr} z_n) einv_R            (+ r.z partials)
+// Couplings across z-slabs are dropped (block-Jacobi over slabs), so
+// no extra halo exchange is needed; iteration counts may rise with the slab count.
+__device__ __forceinline__ int cell_parity(const Geo& g, long long idx, int& k_out) {
+  const int i = (int)(idx % g.nx);
+  const long long t = idx / g.nx;
+  const int j = (int)(t % g.ny);
+  const int k = (int)(t / g.ny);
+  k_out = k;
+  return (i + j + k + g.z0) & 1;
+}
+
+// step 1: contrib_j = (1 + tau (nfl_j - 1)) / N_j on red Fluid cells, 0 elsewhere
+template <typename T>
+__global__ void k_rb_contrib(Geo g, const uint8_t* __restrict__ codes,
+                             const uint8_t* __restrict__ media, T* __restrict__ contrib,
+                             double tau) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int k;
+    const int par = cell_parity(g, idx, k);
+    const unsigned c = codes[idx];
+    T out = T(0);
+    const int N = __popc(c & 63u);
+    if ((c & B_FLUID) && par == 0 && N > 0) {
+      int nfl = 0;   // Fluid neighbours inside this slab
+      if ((c & B_XM) && media[idx - 1] == FLUID) ++nfl;
+      if ((c & B_XP) && media[idx + 1] == FLUID) ++nfl;
+      if ((c & B_YM) && media[idx - g.nx] == FLUID) ++nfl;
+      if ((c & B_YP) && media[idx + g.nx] == FLUID) ++nfl;
+      if ((c & B_ZM) && k > 0 && media[idx - g.plane] == FLUID) ++nfl;
+      if ((c & B_ZP) && k < g.nz - 1 && media[idx + g.plane] == FLUID) ++nfl;
+      out = (T)((1.0 + tau * (double)(nfl - 1)) / (double)N);
+    }
+    contrib[idx] = out;
+  }
+}
+
+// step 2: einv = 1 / E on Fluid cells, 0 elsewhere
+template <typename T>
+__global__ void k_rb_einv(Geo g, const uint8_t* __restrict__ codes,
+                          const T* __restrict__ contrib, T* __restrict__ einv, double safety) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int k;
+    const int par = cell_parity(g, idx, k);
+    const unsigned c = codes[idx];
+    const int N = __popc(c & 63u);
+    T out = T(0);
+    if ((c & B_FLUID) && N > 0) {
+      double E = (double)N;
+      if (par == 1) {
+        double acc = 0.0;
+        if (c & B_XM) acc += (double)contrib[idx - 1];
+        if (c & B_XP) acc += (double)contrib[idx + 1];
+        if (c & B_YM) acc += (double)contrib[idx - g.nx];
+        if (c & B_YP) acc += (double)contrib[idx + g.nx];
+        if ((c & B_ZM) && k > 0) acc += (double)contrib[idx - g.plane];
+        if ((c & B_ZP) && k < g.nz - 1) acc += (double)contrib[idx + g.plane];
+        const double eb = (double)N - acc;
+        E = (eb < safety * (double)N) ? (double)N : eb;
+      }
+      out = (T)(1.0 / E);
+    }
+    einv[idx] = out;
+  }
+}
+
+// one half sweep; COLOR = 1 black (reads r of red neighbours), 0 red (reads z of
+// black neighbours and reduces r.z over every cell)
+template <typename T, int COLOR>
+__global__ void __launch_bounds__(256)
+k_rb_sweep(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ r,
+           const T* __restrict__ einv, T* __restrict__ z, Scal* __restrict__ sc,
+           double* __restrict__ partials, int par_slot) {
+  __shared__ double red[32];
+  if (sc->done) return;
+  double acc = 0.0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int k;
+    const int par = cell_parity(g, idx, k);
+    const unsigned c = codes[idx];
+    if (par == COLOR) {
+      T zz = T(0);
+      if (c & B_FLUID) {
+        const bool zm = (c & B_ZM) && k > 0, zp = (c & B_ZP) && k < g.nz - 1;
+        T sum = T(0);
+        if (COLOR == 1) {
+          if (c & B_XM) sum += r[idx - 1] * einv[idx - 1];
+          if (c & B_XP) sum += r[idx + 1] * einv[idx + 1];
+          if (c & B_YM) sum += r[idx - g.nx] * einv[idx - g.nx];
+          if (c & B_YP) sum += r[idx + g.nx] * einv[idx + g.nx];
+          if (zm) sum += r[idx - g.plane] * einv[idx - g.plane];
+          if (zp) sum += r[idx + g.plane] * einv[idx + g.plane];
+        } else {
+          if (c & B_XM) sum += z[idx - 1];
+          if (c & B_XP) sum += z[idx + 1];
+          if (c & B_YM) sum += z[idx - g.nx];
+          if (c & B_YP) sum += z[idx + g.nx];
+          if (zm) sum += z[idx - g.plane];
+          if (zp) sum += z[idx + g.plane];
+        }
+        zz = (r[idx] + sum) * einv[idx];
+      }
+      z[idx] = zz;
+      if (COLOR == 0) acc += (double)r[idx] * (double)zz;
+    } else if (COLOR == 0) {
+      acc += (double)r[idx] * (double)z[idx];   // black cells, written by the black sweep
+    }
+  }
+  if (COLOR == 0) {
+    const double bs = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    if (last_block(&sc->ticketC, gridDim.x)) {
+      double t = 0.0;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(partials + b);
+      t = block_sum(t, red);
+      if (threadIdx.x == 0) sc->gBM[par_slot][sc->rank][0] = t;
+    }
+  }
+}
+
 // ---- deferred pressure update ----------------------------------------------------
 // Iteration it leaves its search direction in ring buffer it % m and its step
 // length in alpha_hist[it % m]; this kernel adds every pending term

@@ -103,7 +103,7 @@ SMALL_SCENES = {
 
 
 @pytest.mark.parametrize("name", sorted(SMALL_SCENES))
-@pytest.mark.parametrize("precond", ["none", "jacobi"])
+@pytest.mark.parametrize("precond", ["none", "jacobi", "rbic0"])
 def test_project_fp64_matches_direct_solve(name, precond):
     sc = SMALL_SCENES[name](np.float64)
     lab, U, V, W = fields(sc, np.float64)
@@ -133,6 +133,26 @@ def test_pcg_iteration_count_matches_oracle(name):
     _, oinfo = dr.pcg(lab, b, dr.PC_JACOBI, tol=1e-8)
     assert abs(info["iters"] - oinfo["iters"]) <= 2, (info["iters"], oinfo["iters"])
     assert info["b_inf"] == pytest.approx(oinfo["b_inf"], rel=1e-13)
+
+
+@pytest.mark.parametrize("name", sorted(SMALL_SCENES))
+@pytest.mark.parametrize("tau", [0.0, 0.5])
+def test_rbic0_iteration_count_matches_oracle_and_beats_jacobi(name, tau):
+    """SPL_PC_RBIC0 (the parallel stand-in for MIC(0)): same
+    iterates as oracle/dense_ref.py apply_rbic0, fewer iterations than Jacobi."""
+    sc = SMALL_SCENES[name](np.float64)
+    lab, U, V, W = fields(sc, np.float64)
+    with solver_for(sc, dtype=np.float64, tol=1e-8, precond="rbic0", tau=tau) as s:
+        s.upload(lab, U, V, W)
+        info = s.project(sc["dt"])
+    with solver_for(sc, dtype=np.float64, tol=1e-8, precond="jacobi") as s:
+        s.upload(lab, U, V, W)
+        jinfo = s.project(sc["dt"])
+    b = dr.rhs(lab, U, V, W, sc["dt"], sc["h"], sc["rho"])
+    _, oinfo = dr.pcg(lab, b, dr.PC_RBIC0, tol=1e-8, tau=tau)
+    assert abs(info["iters"] - oinfo["iters"]) <= 2, (info["iters"], oinfo["iters"])
+    assert info["iters"] <= jinfo["iters"]
+    assert info["max_abs_div"] <= 1e-6 * vscale(U, V, W)
 
 
 @pytest.mark.parametrize("name", sorted(SMALL_SCENES))
