@@ -296,7 +296,7 @@ def run_cuda(args):
     gbs_x = cells_local * BYTES_XFLUSH / (ms_x * 1e-3) / 1e9 if ms_x > 0 else 0.0
     dom = "k_phaseB" if ms_b >= ms_a else "k_phaseA"
     dom_gbs = gbs_b if dom == "k_phaseB" else gbs_a
-    step_bytes = cells_local * (71 + args.pcg_iters * BYTES_ITER)
+    step_bytes = cells_local * (75 + args.pcg_iters * BYTES_ITER)
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
 
     # ---- one run-to-tolerance step (iteration count) ------------------------
@@ -350,7 +350,7 @@ def run_cuda(args):
                                      "k_xflush": {"ms": ms_x, "bytes_per_cell": BYTES_XFLUSH,
                                                   "every_iters": NSBUF, "GBps": gbs_x,
                                                   "frac": gbs_x / peak}},
-                         "whole_step": {"bytes_per_cell": 71 + args.pcg_iters * BYTES_ITER,
+                         "whole_step": {"bytes_per_cell": 75 + args.pcg_iters * BYTES_ITER,
                                         "GBps": step_gbs, "frac": step_gbs / peak}},
             "clocks": clocks,
             "to_tolerance": tol_run,
