@@ -1,0 +1,403 @@
+// splashy_host.cpp -- see splashy_host.hpp.  Also exports a small C interface
+// (splh_*) so the pytest suite can drive this C++ host the way the reference's
+// NUnit fixture drives the F# modules (tests/splashy.Tests/Tests.fs:39-52).
+#include "splashy_host.hpp"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "../../include/splashy_cuda.h"
+
+namespace splashy {
+
+// ---- Vector.fs ----------------------------------------------------------------
+Vector3d::Vector3d(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {
+  if (!(std::isfinite(x) && std::isfinite(y) && std::isfinite(z)))   // Vector.fs:15-18
+    throw Failure("Vector3d has an invalid quantity: either NaN or ±Infinity.");
+}
+
+// ---- Coord.fs -------------------------------------------------------------------
+int Coord::nearest(int n) {                       // Coord.fs:49-57 (.NET % truncates like C++)
+  const int h = Constants::h_int;
+  const int r = n % h;
+  if (r == 0) return n;
+  if (r >= h / 2) return n + (h - r);
+  return n - r;
+}
+Coord Coord::construct(int x, int y, int z) { return {nearest(x), nearest(y), nearest(z)}; }
+Coord Coord::construct(double x, double y, double z) {   // round (banker's) -> int -> nearest
+  auto f = [](double v) { return nearest((int)std::nearbyint(v)); };
+  return {f(x), f(y), f(z)};
+}
+std::vector<std::pair<CoordDirection, Coord>> Coord::backward_neighbors() const {
+  const int h = Constants::h_int;
+  return {{CoordDirection::NegX, {x - h, y, z}},
+          {CoordDirection::NegY, {x, y - h, z}},
+          {CoordDirection::NegZ, {x, y, z - h}}};
+}
+std::vector<std::pair<CoordDirection, Coord>> Coord::forward_neighbors() const {
+  const int h = Constants::h_int;
+  return {{CoordDirection::PosX, {x + h, y, z}},
+          {CoordDirection::PosY, {x, y + h, z}},
+          {CoordDirection::PosZ, {x, y, z + h}}};
+}
+std::vector<std::pair<CoordDirection, Coord>> Coord::neighbors() const {
+  auto f = forward_neighbors();
+  auto b = backward_neighbors();
+  f.insert(f.end(), b.begin(), b.end());
+  return f;
+}
+Coord Coord::get_neighbor(CoordDirection d) const {
+  const int h = Constants::h_int;
+  switch (d) {
+    case CoordDirection::NegX: return {x - h, y, z};
+    case CoordDirection::PosX: return {x + h, y, z};
+    case CoordDirection::NegY: return {x, y - h, z};
+    case CoordDirection::PosY: return {x, y + h, z};
+    case CoordDirection::NegZ: return {x, y, z - h};
+    default: return {x, y, z + h};
+  }
+}
+
+// ---- Grid.fs ----------------------------------------------------------------------
+std::optional<Cell> Grid::get(const Coord& where) const {
+  auto it = cells_.find(where);
+  if (it == cells_.end()) return std::nullopt;
+  return it->second;
+}
+const Cell& Grid::raw_get(const Coord& where) const {
+  auto it = cells_.find(where);
+  if (it == cells_.end()) throw Failure("Option.get: no cell at this coordinate.");
+  return it->second;
+}
+std::vector<Coord> Grid::filter(const std::function<bool(const Cell&)>& fn) const {
+  std::vector<Coord> out;
+  for (const auto& kv : cells_)
+    if (fn(kv.second)) out.push_back(kv.first);
+  return out;
+}
+void Grid::set(const Coord& where, const Cell& c) {
+  auto it = cells_.find(where);
+  if (it == cells_.end()) throw Failure("Tried to set non-existent cell.");   // Grid.fs:35
+  it->second = c;
+  ++version_;
+}
+void Grid::add_cells(const std::vector<std::pair<Coord, Cell>>& cells) {
+  for (const auto& kv : cells) {
+    if (!cells_.emplace(kv.first, kv.second).second)
+      throw Failure("An item with the same key has already been added.");
+  }
+  ++version_;
+}
+void Grid::delete_cells(const std::vector<Coord>& cells) {
+  for (const auto& c : cells) cells_.erase(c);
+  ++version_;
+}
+void Grid::update_velocities(const std::vector<std::pair<Coord, Vector3d>>& v) {
+  for (const auto& kv : v) {                       // Grid.fs:49-53
+    Cell c = raw_get(kv.first);
+    c.velocity = kv.second;
+    set(kv.first, c);
+  }
+}
+void Grid::update_pressures(const std::vector<std::pair<Coord, double>>& p) {
+  for (const auto& kv : p) {                       // Grid.fs:55-59
+    Cell c = raw_get(kv.first);
+    c.pressure = kv.second;
+    set(kv.first, c);
+  }
+}
+void Grid::update_media(const std::vector<std::pair<Coord, Media>>& m) {
+  for (const auto& kv : m) {
+    Cell c = raw_get(kv.first);
+    c.media = kv.second;
+    set(kv.first, c);
+  }
+}
+
+// ---- packing ------------------------------------------------------------------------
+long Box::index(const Coord& c) const {
+  const int h = Constants::h_int;
+  const int i = c.x / h - ox, j = c.y / h - oy, k = c.z / h - oz;
+  if (i < 0 || i >= nx || j < 0 || j >= ny || k < 0 || k >= nz) return -1;
+  return ((long)k * ny + j) * nx + i;
+}
+
+Box pack(const Grid& g) {
+  const int h = Constants::h_int;
+  Box b;
+  if (g.size() == 0) throw Failure("cannot pack an empty grid");
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (const auto& kv : g.cells()) {
+    const int c[3] = {kv.first.x / h, kv.first.y / h, kv.first.z / h};
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = std::min(lo[a], c[a]);
+      hi[a] = std::max(hi[a], c[a]);
+    }
+  }
+  b.ox = lo[0]; b.oy = lo[1]; b.oz = lo[2];
+  b.nx = hi[0] - lo[0] + 1; b.ny = hi[1] - lo[1] + 1; b.nz = hi[2] - lo[2] + 1;
+  const size_t n = (size_t)b.nx * b.ny * b.nz;
+  b.media.assign(n, SPL_ABSENT);
+  b.u.assign(n, 0.0); b.v.assign(n, 0.0); b.w.assign(n, 0.0); b.p.assign(n, 0.0);
+  for (const auto& kv : g.cells()) {
+    const long idx = b.index(kv.first);
+    const Cell& c = kv.second;
+    b.media[idx] = (uint8_t)c.media;
+    b.u[idx] = c.velocity.x;          // +face convention, Pressure.fs:18-31
+    b.v[idx] = c.velocity.y;
+    b.w[idx] = c.velocity.z;
+    b.p[idx] = c.pressure.value_or(0.0);
+  }
+  return b;
+}
+
+// ---- Solver ---------------------------------------------------------------------------
+Solver::Solver(unsigned quirks, double tol, int device)
+    : quirks_(quirks), tol_(tol), device_(device) {}
+
+Solver::~Solver() {
+  if (ctx_) spl_destroy(ctx_);
+}
+
+void Solver::fail_if(int rc) {
+  if (rc != SPL_OK) throw Failure(spl_last_error(ctx_));   // text mirrors the failwith strings
+}
+
+void Solver::sync(const Grid& g) {
+  Box b = pack(g);
+  if (!ctx_ || b.nx != box_.nx || b.ny != box_.ny || b.nz != box_.nz || b.ox != box_.ox ||
+      b.oy != box_.oy || b.oz != box_.oz) {
+    if (ctx_) spl_destroy(ctx_);
+    ctx_ = nullptr;
+    spl_desc d;
+    spl_desc_default(&d);
+    d.nx = b.nx; d.ny = b.ny; d.nz = b.nz;
+    d.dtype = SPL_F64;                     // the reference is fp64 (Vector.fs:11-13)
+    d.tol = tol_;                          // the reference solves exactly (Pressure.fs:69)
+    d.quirks = quirks_;
+    d.origin[0] = b.ox; d.origin[1] = b.oy; d.origin[2] = b.oz;
+    d.device = device_;
+    const int rc = spl_create(&ctx_, &d);
+    if (rc != SPL_OK) throw Failure(spl_last_error(nullptr));
+  }
+  box_ = std::move(b);
+  fail_if(spl_upload(ctx_, box_.media.data(), box_.u.data(), box_.v.data(), box_.w.data(),
+                     box_.p.data()));
+  projected_ = false;
+}
+
+void Solver::download() {
+  fail_if(spl_download(ctx_, box_.u.data(), box_.v.data(), box_.w.data(), box_.p.data(),
+                       nullptr));
+}
+
+std::vector<std::pair<Coord, Vector3d>> Solver::convection_apply(
+    const Grid& g, const std::vector<Coord>& markers, double dt) {
+  sync(g);
+  spl_info info;
+  fail_if(spl_advect(ctx_, dt, &info));    // SPL_E_TRACE -> "Backwards particle trace went too far."
+  download();
+  std::vector<std::pair<Coord, Vector3d>> out;
+  for (const Coord& m : markers) {
+    const long idx = box_.index(m);
+    if (idx < 0) throw Failure("Option.get: no cell at this coordinate.");
+    out.emplace_back(m, Vector3d(box_.u[idx], box_.v[idx], box_.w[idx]));
+  }
+  return out;
+}
+
+std::vector<std::pair<Coord, Vector3d>> Solver::forces_apply(
+    const Grid& g, const std::vector<Coord>& markers, double dt) {
+  sync(g);
+  fail_if(spl_add_forces(ctx_, dt));
+  download();
+  std::vector<std::pair<Coord, Vector3d>> out;
+  for (const Coord& m : markers) {
+    const long idx = box_.index(m);
+    if (idx < 0) throw Failure("Option.get: no cell at this coordinate.");
+    out.emplace_back(m, Vector3d(box_.u[idx], box_.v[idx], box_.w[idx]));
+  }
+  return out;
+}
+
+double Solver::pressure_divergence(const Grid& g, const Coord& where) {
+  g.raw_get(where);
+  for (const auto& n : where.neighbors()) g.raw_get(n.second);   // Pressure.fs:14 raw_get throws
+  // the divergence is reported on Fluid cells; the reference evaluates it for any
+  // cell, so the queried cell is packed as Fluid for this call
+  sync(g);
+  const long idx = box_.index(where);
+  std::vector<uint8_t> media = box_.media;
+  media[idx] = SPL_FLUID;
+  fail_if(spl_upload(ctx_, media.data(), box_.u.data(), box_.v.data(), box_.w.data(), nullptr));
+  std::vector<double> div(box_.u.size());
+  fail_if(spl_download(ctx_, nullptr, nullptr, nullptr, nullptr, div.data()));
+  return div[idx];
+}
+
+std::vector<std::pair<Coord, double>> Solver::pressure_calculate(
+    const Grid& g, const std::vector<Coord>& markers, double dt) {
+  sync(g);
+  spl_info info;
+  fail_if(spl_project(ctx_, dt, &info));   // solve + gradient on the device
+  last_iters_ = info.iters;
+  download();
+  projected_ = true;
+  projected_version_ = g.version();
+  std::vector<std::pair<Coord, double>> out;
+  for (const Coord& m : markers) {
+    const long idx = box_.index(m);
+    if (idx < 0) throw Failure("Option.get: no cell at this coordinate.");
+    out.emplace_back(m, box_.p[idx]);
+  }
+  return out;
+}
+
+std::vector<std::pair<Coord, Vector3d>> Solver::pressure_apply(
+    const Grid& g, const std::vector<Coord>& markers, double /*dt*/) {
+  if (!projected_) throw Failure("Pressure.apply before Pressure.calculate");
+  (void)g;
+  // the projected velocities were produced by spl_project; every face the
+  // projection may touch (markers and their -neighbours) is returned once
+  std::vector<Coord> touched;
+  auto push = [&](const Coord& c) {
+    if (std::find(touched.begin(), touched.end(), c) == touched.end()) touched.push_back(c);
+  };
+  for (const Coord& m : markers) {
+    push(m);
+    for (const auto& n : m.backward_neighbors()) push(n.second);
+  }
+  std::vector<std::pair<Coord, Vector3d>> out;
+  for (const Coord& c : touched) {
+    const long idx = box_.index(c);
+    if (idx < 0 || box_.media[idx] == SPL_ABSENT) continue;
+    out.emplace_back(c, Vector3d(box_.u[idx], box_.v[idx], box_.w[idx]));
+  }
+  return out;
+}
+
+void Solver::check(const Grid& g, const std::vector<Coord>& markers) {
+  (void)markers;
+  sync(g);
+  spl_info info;
+  fail_if(spl_check(ctx_, 0.0001, &info));   // Pressure.fs:148 threshold
+}
+
+}  // namespace splashy
+
+// ---------------------------------------------------------------------------------------
+// C interface for the test-suite (ctypes)
+// ---------------------------------------------------------------------------------------
+using namespace splashy;
+
+namespace {
+thread_local std::string g_err;
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+struct Host {
+  Grid grid;
+  std::unique_ptr<Solver> solver;
+};
+std::vector<Coord> coords_of(const int* xyz, int n) {
+  std::vector<Coord> out;
+  for (int i = 0; i < n; ++i) out.push_back({xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
+  return out;
+}
+}  // namespace
+
+extern "C" {
+
+const char* splh_last_error(void) { return g_err.c_str(); }
+
+void* splh_new(unsigned quirks, double tol) {
+  Host* h = new Host();
+  h->solver.reset(new Solver(quirks, tol));
+  return h;
+}
+void splh_free(void* h) { delete static_cast<Host*>(h); }
+
+int splh_nearest(int n) { return Coord::nearest(n); }
+void splh_construct_float(double x, double y, double z, int* out) {
+  const Coord c = Coord::construct(x, y, z);
+  out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
+
+int splh_add_cell(void* hp, int x, int y, int z, int media, double vx, double vy, double vz,
+                  int has_p, double p) {
+  return guarded([&] {
+    Cell c;
+    c.media = (Media)media;
+    c.velocity = Vector3d(vx, vy, vz);
+    if (has_p) c.pressure = p;
+    static_cast<Host*>(hp)->grid.add_cells({{Coord{x, y, z}, c}});
+  });
+}
+int splh_get_cell(void* hp, int x, int y, int z, int* media, double* vel, int* has_p, double* p) {
+  return guarded([&] {
+    const Cell& c = static_cast<Host*>(hp)->grid.raw_get({x, y, z});
+    *media = (int)c.media;
+    vel[0] = c.velocity.x; vel[1] = c.velocity.y; vel[2] = c.velocity.z;
+    *has_p = c.pressure.has_value();
+    *p = c.pressure.value_or(0.0);
+  });
+}
+int splh_size(void* hp) { return (int)static_cast<Host*>(hp)->grid.size(); }
+int splh_update_velocity(void* hp, int x, int y, int z, double vx, double vy, double vz) {
+  return guarded([&] {
+    static_cast<Host*>(hp)->grid.update_velocities({{Coord{x, y, z}, Vector3d(vx, vy, vz)}});
+  });
+}
+int splh_update_media(void* hp, int x, int y, int z, int media) {
+  return guarded([&] { static_cast<Host*>(hp)->grid.update_media({{Coord{x, y, z}, (Media)media}}); });
+}
+
+// Pressure.divergence coord
+int splh_pressure_divergence(void* hp, int x, int y, int z, double* out) {
+  Host* h = static_cast<Host*>(hp);
+  return guarded([&] { *out = h->solver->pressure_divergence(h->grid, {x, y, z}); });
+}
+// Convection.apply markers dt |> Grid.update_velocities      (Simulator.fs:82)
+int splh_convection(void* hp, const int* markers, int n, double dt) {
+  Host* h = static_cast<Host*>(hp);
+  return guarded([&] {
+    h->grid.update_velocities(h->solver->convection_apply(h->grid, coords_of(markers, n), dt));
+  });
+}
+// Forces.apply markers dt |> Grid.update_velocities          (Simulator.fs:84)
+int splh_forces(void* hp, const int* markers, int n, double dt) {
+  Host* h = static_cast<Host*>(hp);
+  return guarded([&] {
+    h->grid.update_velocities(h->solver->forces_apply(h->grid, coords_of(markers, n), dt));
+  });
+}
+// Pressure.calculate |> update_pressures ; Pressure.apply |> update_velocities (:88-89)
+int splh_pressure(void* hp, const int* markers, int n, double dt, int* iters) {
+  Host* h = static_cast<Host*>(hp);
+  return guarded([&] {
+    const auto ms = coords_of(markers, n);
+    const auto ps = h->solver->pressure_calculate(h->grid, ms, dt);
+    const auto vs = h->solver->pressure_apply(h->grid, ms, dt);
+    h->grid.update_pressures(ps);
+    h->grid.update_velocities(vs);
+    if (iters) *iters = h->solver->last_iterations();
+  });
+}
+// Pressure.check_pressures ; Pressure.check_divergence        (Simulator.fs:91-97)
+int splh_checks(void* hp, const int* markers, int n) {
+  Host* h = static_cast<Host*>(hp);
+  return guarded([&] { h->solver->check(h->grid, coords_of(markers, n)); });
+}
+
+}  // extern "C"

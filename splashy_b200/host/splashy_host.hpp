@@ -1,0 +1,147 @@
+// splashy_host.hpp -- C++ mirror of the reference's solver-facing API
+// (src/splashy/{Coord,Cell,Grid,Convection,Forces,Pressure}.fs) on top of the C ABI
+// of libsplashy_cuda.so.  The reference host is F# (compiled code) and no .NET
+// toolchain exists in this image, so this is the compiled host side: same module
+// and function names, argument meaning and error behaviour (std::runtime_error
+// carrying the reference's failwith text), with the three hot functions executed
+// on the GPU.  State stays in a sparse Dictionary-like Grid exactly as in
+// Grid.fs:12; every GPU call packs it into the dense box.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+struct spl_ctx;
+
+namespace splashy {
+
+// Constants.fs:10-36
+namespace Constants {
+constexpr int h_int = 10;
+constexpr double h = 10.0;
+constexpr double fluid_density = 999.97;
+constexpr double atmospheric_pressure = 0.0;
+constexpr double gravity[3] = {0.0, -9.81, 0.0};
+}  // namespace Constants
+
+struct Failure : std::runtime_error {      // the reference's failwith -> System.Exception
+  using std::runtime_error::runtime_error;
+};
+
+// Vector.fs:9-34
+struct Vector3d {
+  double x = 0, y = 0, z = 0;
+  Vector3d() = default;
+  Vector3d(double x_, double y_, double z_);   // throws on NaN / +-Inf (Vector.fs:15-18)
+};
+
+enum class CoordDirection { NegX, NegY, NegZ, PosX, PosY, PosZ };   // Coord.fs:12
+
+// Coord.fs:18-92
+struct Coord {
+  int x = 0, y = 0, z = 0;
+  bool operator==(const Coord& o) const { return x == o.x && y == o.y && z == o.z; }
+  static int nearest(int n);                               // Coord.fs:49-57
+  static Coord construct(int x, int y, int z);             // Coord.fs:59-61
+  static Coord construct(double x, double y, double z);    // Coord.fs:65-67
+  std::vector<std::pair<CoordDirection, Coord>> backward_neighbors() const;
+  std::vector<std::pair<CoordDirection, Coord>> forward_neighbors() const;
+  std::vector<std::pair<CoordDirection, Coord>> neighbors() const;   // forward, then backward
+  Coord get_neighbor(CoordDirection d) const;
+};
+struct CoordHash {                                          // Coord.fs:23-24
+  size_t operator()(const Coord& c) const { return (size_t)(541 * c.x + 79 * c.y + 31 * c.z); }
+};
+
+enum class Media : uint8_t { Air = 0, Fluid = 1, Solid = 2 };   // Cell.fs:9
+
+struct Cell {                                                // Cell.fs:11-16
+  Media media = Media::Air;
+  Vector3d velocity;                 // on the +faces
+  std::optional<double> pressure;
+  bool is_solid() const { return media == Media::Solid; }
+  bool is_not_solid() const { return media != Media::Solid; }
+};
+
+// Grid.fs:12-59 (an instance instead of the reference's module-level mutable)
+class Grid {
+ public:
+  std::optional<Cell> get(const Coord& where) const;
+  const Cell& raw_get(const Coord& where) const;           // throws when absent
+  std::vector<Coord> filter(const std::function<bool(const Cell&)>& fn) const;
+  void add_cells(const std::vector<std::pair<Coord, Cell>>& cells);
+  void delete_cells(const std::vector<Coord>& cells);
+  void update_velocities(const std::vector<std::pair<Coord, Vector3d>>& v);
+  void update_pressures(const std::vector<std::pair<Coord, double>>& p);
+  void update_media(const std::vector<std::pair<Coord, Media>>& m);   // Tests.fs:69
+  size_t size() const { return cells_.size(); }
+  uint64_t version() const { return version_; }
+  const std::unordered_map<Coord, Cell, CoordHash>& cells() const { return cells_; }
+
+ private:
+  void set(const Coord& where, const Cell& c);             // Grid.fs:33-36
+  std::unordered_map<Coord, Cell, CoordHash> cells_;
+  uint64_t version_ = 0;
+};
+
+// dense box packed from the grid
+struct Box {
+  int nx = 0, ny = 0, nz = 0, ox = 0, oy = 0, oz = 0;
+  std::vector<uint8_t> media;
+  std::vector<double> u, v, w, p;
+  long index(const Coord& c) const;      // -1 when outside
+};
+Box pack(const Grid& g);
+
+// The solver terms that run on the GPU.  One Solver = one spl_ctx (recreated when
+// the packed box changes shape); fp64 like the reference.
+class Solver {
+ public:
+  explicit Solver(unsigned quirks = 0, double tol = 1e-12, int device = 0);
+  ~Solver();
+  Solver(const Solver&) = delete;
+  Solver& operator=(const Solver&) = delete;
+
+  // Convection.apply (Convection.fs:60-66): returned, not committed
+  std::vector<std::pair<Coord, Vector3d>> convection_apply(const Grid& g,
+                                                           const std::vector<Coord>& markers,
+                                                           double dt);
+  // Forces.apply (Forces.fs:6-12)
+  std::vector<std::pair<Coord, Vector3d>> forces_apply(const Grid& g,
+                                                       const std::vector<Coord>& markers,
+                                                       double dt);
+  // Pressure.divergence (Pressure.fs:16-32)
+  double pressure_divergence(const Grid& g, const Coord& where);
+  // Pressure.calculate (Pressure.fs:41-72)
+  std::vector<std::pair<Coord, double>> pressure_calculate(const Grid& g,
+                                                           const std::vector<Coord>& markers,
+                                                           double dt);
+  // Pressure.apply (Pressure.fs:115-129); must follow pressure_calculate on the same
+  // grid state.  Each touched face is returned once.
+  std::vector<std::pair<Coord, Vector3d>> pressure_apply(const Grid& g,
+                                                         const std::vector<Coord>& markers,
+                                                         double dt);
+  // Pressure.check_pressures + check_divergence (Pressure.fs:132-149)
+  void check(const Grid& g, const std::vector<Coord>& markers);
+  int last_iterations() const { return last_iters_; }
+
+ private:
+  void sync(const Grid& g);          // pack + (re)create + upload
+  void download();
+  void fail_if(int rc);
+  spl_ctx* ctx_ = nullptr;
+  Box box_;
+  unsigned quirks_;
+  double tol_;
+  int device_;
+  int last_iters_ = 0;
+  bool projected_ = false;
+  uint64_t projected_version_ = 0;
+};
+
+}  // namespace splashy
