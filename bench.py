@@ -58,6 +58,20 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel: str, n: int):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r1_traffic.json, taken at 512^3); None for any other size."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if n != 512 or not p.exists():
+        return None
+    try:
+        t = json.loads(p.read_text())
+        key = "k_phaseA_ring" if kernel == "k_phaseA" else kernel
+        return float(t[key]["dram_bytes"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -341,7 +355,10 @@ def run_cuda(args):
                     "result_checksum": checksum},
             "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+                         "unit": "GB/s", "frac": dom_gbs / peak,
+                         "traffic": ncu_traffic(dom, n),
+                         "algorithmic_bytes": cells_local * (BYTES_PHASE_B if dom == "k_phaseB"
+                                                             else BYTES_PHASE_A),
                          "peak_source": peak_src,
                          "kernels": {"k_phaseA": {"ms": ms_a, "bytes_per_cell": BYTES_PHASE_A,
                                                   "GBps": gbs_a, "frac": gbs_a / peak},
