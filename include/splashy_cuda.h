@@ -82,6 +82,7 @@ typedef struct spl_desc {
   const void* nccl_id;     /* world > 1: 128-byte ncclUniqueId from
                               spl_nccl_unique_id, identical on every rank     */
   double   gravity[3];     /* Constants.fs:26, used by spl_add_forces         */
+  double   viscosity;      /* Constants.fs:13 fluid_viscosity (kinematic)     */
 } spl_desc;
 
 /* result block (SURVEY.md section 5 "metrics")                              */
@@ -128,6 +129,17 @@ int  spl_download(spl_ctx* ctx, void* u, void* v, void* w, void* p, void* div);
 int  spl_advect(spl_ctx* ctx, double dt, spl_info* info);
 /* Forces.apply (Forces.fs:6-12, Simulator.fs:84): v += gravity * dt on Fluid */
 int  spl_add_forces(spl_ctx* ctx, double dt);
+/* Viscosity.apply (Viscosity.fs:12-36, Simulator.fs:86) as a Jacobi update;
+ * quirk Q10 of SURVEY.md kept (no 1/h^2, always -6 v, sign-gated neighbours)  */
+int  spl_add_viscosity(spl_ctx* ctx, double dt);
+/* Build.cleanup (Simulator.fs:100-110): propagate velocities into the 2-layer
+ * buffer (Build.fs:105-141, order-free reading -- DESIGN.md), zero components
+ * pointing into Solid cells (Build.fs:144-160), zero Solid velocities          */
+int  spl_cleanup(spl_ctx* ctx);
+/* the solver part of Simulator.advance (Simulator.fs:82-110): advect, forces,
+ * viscosity, project (+ checks with the reference's 1e-4 threshold when
+ * `sanity` != 0), cleanup                                                      */
+int  spl_advance(spl_ctx* ctx, double dt, int sanity, spl_info* info);
 /* Pressure.divergence over every Fluid cell (Pressure.fs:16-32) -> kept on the
  * device as the PCG right-hand side b = (h rho/dt) * div (Pressure.fs:64-68) */
 int  spl_divergence(spl_ctx* ctx, double dt, spl_info* info);

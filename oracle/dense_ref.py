@@ -441,3 +441,98 @@ def pack_sparse(cells, h: int = 10, margin: int = 0):
         U[k, j, i], V[k, j, i], W[k, j, i] = c.velocity
         P[k, j, i] = c.pressure if c.pressure is not None else 0.0
     return labels, U, V, W, P, tuple(lo)
+
+
+# --------------------------------------------------------------------------
+# "next" rows of SURVEY 8f: viscosity (N1) and post-projection cleanup (N2)
+# --------------------------------------------------------------------------
+def viscosity(labels, U, V, W, dt: float, nu: float = 0.000001):
+    """Viscosity.fs:12-36 as a Jacobi update (SURVEY Q10 kept: no 1/h^2, always
+    -6 v, a neighbour contributes only its d-axis component, only if it is Fluid
+    and that component has the sign of d).  Only Fluid cells change."""
+    t = U.dtype.type
+    fl = labels == FLUID
+    k = t(nu * dt)
+    out = []
+    for axis, F in enumerate((U, V, W)):
+        Fp = _nb(F, axis, +1, 0)            # neighbour on the + side
+        Fm = _nb(F, axis, -1, 0)
+        flp = _nb(fl, axis, +1, False)
+        flm = _nb(fl, axis, -1, False)
+        shared = np.where(flp & (Fp > 0), Fp, t(0)) + np.where(flm & (Fm < 0), Fm, t(0))
+        lap = shared - t(6) * F
+        out.append(np.where(fl, F + lap * k, F).astype(U.dtype))
+    return tuple(out)
+
+
+def zero_solid_velocities(labels, U, V, W):
+    """Build.fs:144-160: for every Solid cell, the -neighbour's +face component is
+    zeroed when that neighbour is non-solid and the component points into the solid
+    (> 0); then Simulator.fs:106-109: every Solid cell's velocity is zeroed."""
+    t = U.dtype.type
+    ns = nonsolid(labels)
+    solid = labels == SOLID
+    out = []
+    for axis, F in enumerate((U, V, W)):
+        solid_p = _nb(solid, axis, +1, False)       # + neighbour is Solid
+        G = np.where(ns & solid_p & (F > 0), t(0), F)
+        G = np.where(solid, t(0), G)
+        out.append(G.astype(U.dtype))
+    return tuple(out)
+
+
+def fluid_layers(labels, max_distance: int = 2):
+    """BFS distance from the Fluid cells through existing cells (Build.fs:79-102
+    layer numbers): 0 on Fluid, 1..max_distance on the buffer, -1 elsewhere."""
+    layer = np.where(labels == FLUID, 0, -1).astype(np.int32)
+    exists = labels != ABSENT
+    for i in range(1, max_distance + 1):
+        near = np.zeros(labels.shape, dtype=bool)
+        for axis in range(3):
+            for d in (-1, +1):
+                near |= _nb(layer == i - 1, axis, d, False)
+        layer = np.where((layer < 0) & exists & near, i, layer)
+    return layer
+
+
+def propagate_velocities(labels, U, V, W, max_distance: int = 2):
+    """Build.fs:105-141, order-free reading.  The reference relabels cells while
+    it enumerates its Dictionary (Layers.set m (Some (i - 1)) inside the loop), so
+    which buffer cells are reached -- and from which neighbours -- depends on the
+    .NET enumeration order; it does read only pre-update velocities (the result
+    list is committed afterwards).  Here the layers are the BFS distances from the
+    Fluid cells, every cell of layer 1..max_distance is updated once from the
+    cells of the previous layer, all from the pre-update field:
+      avg_axis = [own component if the + neighbour is in the previous layer]
+               + [- neighbour's component if it is in the previous layer]
+      component := avg_axis if the neighbour on the side the own component points
+                   to (Build.fs:123-125) exists and is not Fluid, else unchanged.
+    Coincides with the transcription on the stock 7-cell scene."""
+    t = U.dtype.type
+    layer = fluid_layers(labels, max_distance)
+    exists = labels != ABSENT
+    fl = labels == FLUID
+    out = []
+    for axis, F in enumerate((U, V, W)):
+        G = F.copy()
+        for i in range(1, max_distance + 1):
+            cur = layer == i
+            prev = layer == i - 1
+            touched = np.zeros(labels.shape, dtype=bool)
+            for a2 in range(3):
+                touched |= _nb(prev, a2, +1, False) | _nb(prev, a2, -1, False)
+            prev_p = _nb(prev, axis, +1, False)
+            prev_m = _nb(prev, axis, -1, False)
+            avg = np.where(prev_p, F, t(0)) + np.where(prev_m, _nb(F, axis, -1, 0), t(0))
+            neg = F < 0
+            ex_dir = np.where(neg, _nb(exists, axis, -1, False), _nb(exists, axis, +1, False))
+            fl_dir = np.where(neg, _nb(fl, axis, -1, False), _nb(fl, axis, +1, False))
+            G = np.where(cur & touched & ex_dir & ~fl_dir, avg, G)
+        out.append(G.astype(U.dtype))
+    return tuple(out)
+
+
+def cleanup(labels, U, V, W):
+    """Simulator.fs:100-110 (Build.cleanup): propagate, zero into-solid, zero solids."""
+    U, V, W = propagate_velocities(labels, U, V, W)
+    return zero_solid_velocities(labels, U, V, W)

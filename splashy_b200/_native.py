@@ -45,6 +45,7 @@ class SplDesc(C.Structure):
         ("nz_global", C.c_int), ("z0", C.c_int),
         ("nccl_id", C.c_void_p),
         ("gravity", C.c_double * 3),
+        ("viscosity", C.c_double),
     ]
 
 
@@ -78,6 +79,9 @@ SYMBOLS = {
     "spl_download": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "spl_advect": (C.c_int, [_VP, C.c_double, C.POINTER(SplInfo)]),
     "spl_add_forces": (C.c_int, [_VP, C.c_double]),
+    "spl_add_viscosity": (C.c_int, [_VP, C.c_double]),
+    "spl_cleanup": (C.c_int, [_VP]),
+    "spl_advance": (C.c_int, [_VP, C.c_double, C.c_int, C.POINTER(SplInfo)]),
     "spl_divergence": (C.c_int, [_VP, C.c_double, C.POINTER(SplInfo)]),
     "spl_project": (C.c_int, [_VP, C.c_double, C.POINTER(SplInfo)]),
     "spl_check": (C.c_int, [_VP, C.c_double, C.POINTER(SplInfo)]),

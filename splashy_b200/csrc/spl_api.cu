@@ -110,7 +110,7 @@ struct spl_ctx {
   char* sbuf[MAX_SBUF]{};      // ring of search-direction buffers (plane 0 pointers)
   int nsbuf = 8;               // m: x is updated every m iterations (SPL_NSBUF)
   char *z = nullptr, *einv = nullptr;
-  uint8_t *media = nullptr, *codes = nullptr;
+  uint8_t *media = nullptr, *codes = nullptr, *layer = nullptr;
   Scal* sc = nullptr;          // device
   Scal* hsc = nullptr;         // pinned mirror
   double* partials = nullptr;  // 2 * MAX_PARTIALS
@@ -304,6 +304,39 @@ struct Impl {
     LAUNCH(c, k_forces<T>, grid_for(c, g.ncell), 256, g, c->media, P(c->u), P(c->v), P(c->w),
            T(c->d.gravity[0] * dt), T(c->d.gravity[1] * dt), T(c->d.gravity[2] * dt));
     CU(cudaGetLastError());
+    return SPL_OK;
+  }
+
+  static int viscosity(spl_ctx* c, double dt) {
+    const Geo& g = c->g;
+    int rc = exchange_velocity(c, 1);
+    if (rc) return rc;
+    LAUNCH(c, k_viscosity<T>, grid_for(c, g.ncell), 256, g, c->media, P(c->u), P(c->v), P(c->w),
+           P(c->u2), P(c->v2), P(c->w2), T(c->d.viscosity * dt));
+    CU(cudaGetLastError());
+    std::swap(c->u, c->u2);
+    std::swap(c->v, c->v2);
+    std::swap(c->w, c->w2);
+    return SPL_OK;
+  }
+
+  static int cleanup(spl_ctx* c) {
+    const Geo& g = c->g;
+    const int grid = grid_for(c, g.ncell);
+    int rc;
+    LAUNCH(c, k_layer_init, grid, 256, g, c->media, c->layer);
+    for (int step = 1; step <= 2; ++step) {   // Build.fs:34 max_distance = 2
+      if ((rc = exchange_halo(c, reinterpret_cast<char*>(c->layer), 1, ncclUint8, 1))) return rc;
+      LAUNCH(c, k_layer_step, grid, 256, g, c->media, c->layer, step);
+    }
+    if ((rc = exchange_halo(c, reinterpret_cast<char*>(c->layer), 1, ncclUint8, 1))) return rc;
+    if ((rc = exchange_velocity(c, 1))) return rc;
+    LAUNCH(c, k_cleanup<T>, grid, 256, g, c->media, c->layer, P(c->u), P(c->v), P(c->w),
+           P(c->u2), P(c->v2), P(c->w2));
+    CU(cudaGetLastError());
+    std::swap(c->u, c->u2);
+    std::swap(c->v, c->v2);
+    std::swap(c->w, c->w2);
     return SPL_OK;
   }
 
@@ -570,6 +603,7 @@ void spl_desc_default(spl_desc* d) {
   d->gravity[0] = 0.0;         // Constants.fs:26
   d->gravity[1] = -9.81;
   d->gravity[2] = 0.0;
+  d->viscosity = 0.000001;     // Constants.fs:13
 }
 
 const char* spl_last_error(const spl_ctx* ctx) {
@@ -678,6 +712,8 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   c->media = reinterpret_cast<uint8_t*>(tmp);
   if ((rc = alloc_field(c, 14, 1, &tmp, 0))) return rc;
   c->codes = reinterpret_cast<uint8_t*>(tmp);
+  if ((rc = alloc_field(c, 24, 1, &tmp, 0xFF))) return rc;   // BFS layers (spl_cleanup)
+  c->layer = reinterpret_cast<uint8_t*>(tmp);
   CU(cudaMalloc(&c->sc, sizeof(Scal)));
   CU(cudaMemsetAsync(c->sc, 0, sizeof(Scal), c->stream));
   CU(cudaMalloc(&c->partials, sizeof(double) * 2 * MAX_PARTIALS));
@@ -813,6 +849,28 @@ int spl_add_forces(spl_ctx* c, double dt) {
   return SPL_OK;
 }
 
+int spl_add_viscosity(spl_ctx* c, double dt) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_add_viscosity before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  int rc = DISPATCH(c, Impl<float>::viscosity(c, dt), Impl<double>::viscosity(c, dt));
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_rhs = false;
+  return SPL_OK;
+}
+
+int spl_cleanup(spl_ctx* c) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_cleanup before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  int rc = DISPATCH(c, Impl<float>::cleanup(c), Impl<double>::cleanup(c));
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_rhs = false;
+  return SPL_OK;
+}
+
 int spl_divergence(spl_ctx* c, double dt, spl_info* info) {
   if (!c) return SPL_E_BADARG;
   if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_divergence before spl_upload");
@@ -894,6 +952,40 @@ int spl_step(spl_ctx* c, double dt, spl_info* info) {
   if (!c) return SPL_E_BADARG;
   if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_step before spl_upload");
   return project_impl(c, dt, info, true);
+}
+
+int spl_advance(spl_ctx* c, double dt, int sanity, spl_info* info) {
+  if (!c) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_advance before spl_upload");
+  if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
+  CU(cudaSetDevice(c->d.device));
+  // Simulator.fs:82-86: convection, forces, viscosity (advect's error checks need the
+  // escape counter, so it goes through the public entry point)
+  spl_info adv;
+  int rc = spl_advect(c, dt, &adv);
+  if (rc) return rc;
+  if ((rc = DISPATCH(c, Impl<float>::forces(c, dt), Impl<double>::forces(c, dt)))) return rc;
+  if ((rc = DISPATCH(c, Impl<float>::viscosity(c, dt), Impl<double>::viscosity(c, dt)))) return rc;
+  // Simulator.fs:88-89 (+ the validators of :91-97 on the device)
+  spl_info local;
+  memset(&local, 0, sizeof local);
+  rc = project_impl(c, dt, &local, false);
+  local.ms_advect = adv.ms_advect;
+  local.ms_total += adv.ms_advect;
+  local.trace_escapes = adv.trace_escapes;
+  local.kernel_launches += adv.kernel_launches + 2;
+  if (info) *info = local;
+  if (rc) return rc;
+  if (sanity) {
+    if (local.nonfinite) return fail(c, SPL_E_NONFINITE, "Invalid pressure.");
+    if (local.max_abs_div > 0.0001)   // Pressure.fs:148
+      return fail(c, SPL_E_DIVERGENCE, "Velocity field is not correct: divergence %g.",
+                  local.max_abs_div);
+  }
+  // Simulator.fs:100-110
+  if ((rc = DISPATCH(c, Impl<float>::cleanup(c), Impl<double>::cleanup(c)))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
 }
 
 int spl_check(spl_ctx* c, double div_tol, spl_info* info) {

@@ -160,4 +160,133 @@ __global__ void k_forces(Geo g, const uint8_t* __restrict__ media, T* __restrict
   }
 }
 
+// ---- viscosity -------------------------------------------------------
+// Viscosity.fs:12-36 as a Jacobi update (quirk Q10 kept: no 1/h^2, always -6 v; a
+// neighbour contributes only its d-axis component, only if it is Fluid and that
+// component has the sign of d).  Reads (u,v,w), writes (u2,v2,w2).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_viscosity(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ u,
+            const T* __restrict__ v, const T* __restrict__ w, T* __restrict__ u2,
+            T* __restrict__ v2, T* __restrict__ w2, T k) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % g.nx);
+    const long long t = idx / g.nx;
+    const int j = (int)(t % g.ny);
+    const int kk = (int)(t / g.ny);
+    const int kg = kk + g.z0;
+    const T* f[3] = {u, v, w};
+    T* o[3] = {u2, v2, w2};
+    const bool fl = media[idx] == FLUID;
+    const bool inm[3] = {i > 0, j > 0, kg > 0};
+    const bool inp[3] = {i < g.nx - 1, j < g.ny - 1, kg < g.nzg - 1};
+    const long long off[3] = {1, (long long)g.nx, g.plane};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const T own = f[a][idx];
+      T val = own;
+      if (fl) {
+        T shared = T(0);
+        if (inp[a] && media[idx + off[a]] == FLUID) {
+          const T n = f[a][idx + off[a]];
+          if (n > T(0)) shared += n;          // Coord.is_bordering PosX: v.x > 0
+        }
+        if (inm[a] && media[idx - off[a]] == FLUID) {
+          const T n = f[a][idx - off[a]];
+          if (n < T(0)) shared += n;          // NegX: v.x < 0
+        }
+        val = own + (shared - T(6) * own) * k;
+      }
+      o[a][idx] = val;
+    }
+  }
+}
+
+// ---- post-projection cleanup ---------------------------------------------
+// BFS layers from the Fluid cells (Build.fs:79-102 numbering): 0 Fluid, 1..2 buffer,
+// 255 elsewhere.  Step i marks the unlabelled existing cells next to layer i-1.
+__global__ void k_layer_init(Geo g, const uint8_t* __restrict__ media,
+                             uint8_t* __restrict__ layer) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x)
+    layer[idx] = (media[idx] == FLUID) ? 0 : 255;
+}
+
+__global__ void k_layer_step(Geo g, const uint8_t* __restrict__ media,
+                             uint8_t* __restrict__ layer, int step) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    if (layer[idx] != 255 || media[idx] == ABSENT) continue;
+    const int i = (int)(idx % g.nx);
+    const long long t = idx / g.nx;
+    const int j = (int)(t % g.ny);
+    const int k = (int)(t / g.ny);
+    const int kg = k + g.z0;
+    const uint8_t want = (uint8_t)(step - 1);
+    bool near = false;
+    near |= (i > 0) && layer[idx - 1] == want;
+    near |= (i < g.nx - 1) && layer[idx + 1] == want;
+    near |= (j > 0) && layer[idx - g.nx] == want;
+    near |= (j < g.ny - 1) && layer[idx + g.nx] == want;
+    near |= (kg > 0) && layer[idx - g.plane] == want;
+    near |= (kg < g.nzg - 1) && layer[idx + g.plane] == want;
+    if (near) layer[idx] = (uint8_t)step;
+  }
+}
+
+// Build.propagate_velocities (order-free reading, see oracle/dense_ref.py) followed
+// by Build.zero_solid_velocities and the "solid velocities are zero" rule
+// (Build.fs:105-160, Simulator.fs:100-110).  Reads (u,v,w), writes (u2,v2,w2).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_cleanup(Geo g, const uint8_t* __restrict__ media, const uint8_t* __restrict__ layer,
+          const T* __restrict__ u, const T* __restrict__ v, const T* __restrict__ w,
+          T* __restrict__ u2, T* __restrict__ v2, T* __restrict__ w2) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % g.nx);
+    const long long t = idx / g.nx;
+    const int j = (int)(t % g.ny);
+    const int k = (int)(t / g.ny);
+    const int kg = k + g.z0;
+    const T* f[3] = {u, v, w};
+    T* o[3] = {u2, v2, w2};
+    const uint8_t m0 = media[idx];
+    const uint8_t l0 = layer[idx];
+    const bool inm[3] = {i > 0, j > 0, kg > 0};
+    const bool inp[3] = {i < g.nx - 1, j < g.ny - 1, kg < g.nzg - 1};
+    const long long off[3] = {1, (long long)g.nx, g.plane};
+    bool touched = false;
+    uint8_t lp[3], lm[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lp[a] = inp[a] ? layer[idx + off[a]] : 255;
+      lm[a] = inm[a] ? layer[idx - off[a]] : 255;
+    }
+    const uint8_t prev = (uint8_t)(l0 - 1);
+    if (l0 >= 1 && l0 != 255) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) touched |= (lp[a] == prev) || (lm[a] == prev);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      T val = f[a][idx];
+      const uint8_t mp = inp[a] ? media[idx + off[a]] : ABSENT;
+      if (touched) {
+        const uint8_t mm = inm[a] ? media[idx - off[a]] : ABSENT;
+        T avg = T(0);
+        if (lp[a] == prev) avg += val;
+        if (lm[a] == prev) avg += f[a][idx - off[a]];
+        const uint8_t md = (val < T(0)) ? mm : mp;       // Build.fs:123-125
+        if (md != ABSENT && md != FLUID) val = avg;
+      }
+      // Build.fs:144-160: a component pointing into a Solid +neighbour is zeroed
+      if (is_nonsolid(m0) && mp == SOLID && val > T(0)) val = T(0);
+      if (m0 == SOLID) val = T(0);                       // Simulator.fs:106-109
+      o[a][idx] = val;
+    }
+  }
+}
+
 }  // namespace spl

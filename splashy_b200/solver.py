@@ -79,7 +79,8 @@ class Solver:
                  device: int = 0, rank: int = 0, world: int = 1,
                  nz_global: int = 0, z0: int = 0,
                  nccl_id: Optional[bytes] = None,
-                 gravity: Sequence[float] = (0.0, -9.81, 0.0)):
+                 gravity: Sequence[float] = (0.0, -9.81, 0.0),
+                 viscosity: float = 0.000001):
         self._lib = nat.load()
         self.dtype = np.dtype(dtype)
         if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
@@ -97,6 +98,7 @@ class Solver:
         d.device = device
         d.rank, d.world, d.nz_global, d.z0 = rank, world, nz_global, z0
         d.gravity[:] = list(gravity)
+        d.viscosity = viscosity
         self._id_buf = None
         if nccl_id is not None:
             self._id_buf = C.create_string_buffer(nccl_id, 128)
@@ -173,6 +175,15 @@ class Solver:
 
     def add_forces(self, dt: float):
         self._check(self._lib.spl_add_forces(self._ctx, dt))
+
+    def add_viscosity(self, dt: float):
+        self._check(self._lib.spl_add_viscosity(self._ctx, dt))
+
+    def cleanup(self):
+        self._check(self._lib.spl_cleanup(self._ctx))
+
+    def advance(self, dt: float, sanity: bool = True) -> Dict:
+        return self._call(self._lib.spl_advance, dt, int(sanity))
 
     def divergence(self, dt: float) -> Dict:
         return self._call(self._lib.spl_divergence, dt)
