@@ -121,6 +121,7 @@ struct spl_ctx {
   int fixed_iters = 0;
   int zchunk_override = 0;
   int ring_attr_set = 0;
+  bool no_2d_view = false;     // SPL_NO_2D_VIEW=1: 2-D boxes use the 3-D tiling
   bool no_ring = false;        // SPL_NO_RING=1: force the generic phase-A kernel
   int64_t launches = 0;
   double rhs_dt = 0.0;
@@ -369,8 +370,27 @@ struct Impl {
         return;
       }
     }
-    LAUNCH(c, (k_phaseA<T, VEC, PC>), gridA, blockA, g, c->codes, zr, sold, snew, P(c->q),
-           c->sc, c->partials, par, zc);
+    LAUNCH(c, (k_phaseA<T, VEC, PC, TILE_Y>), gridA, blockA, g, c->codes, zr, sold, snew,
+           P(c->q), c->sc, c->partials, par, zc);
+  }
+
+  // 2-D box (nz = 1): the same kernel on the view nx x 1 x ny, so it marches along y
+  template <int VEC, int PC>
+  static void launch_phaseA_2d(spl_ctx* c, const T* zr, const T* sold, T* snew, int par) {
+    Geo v = c->g;
+    v.ny = 1;
+    v.nz = c->g.ny;
+    v.nzg = c->g.ny;
+    v.plane = c->g.nx;
+    const int tx = (v.nx + 32 * VEC - 1) / (32 * VEC);
+    int gz = (2048 + tx - 1) / tx;
+    int zc = (v.nz + gz - 1) / gz;
+    if (zc < 16) zc = 16;
+    if (zc > v.nz) zc = v.nz;
+    while ((long long)tx * ((v.nz + zc - 1) / zc) > MAX_PARTIALS) zc *= 2;
+    const dim3 grid(tx, 1, (v.nz + zc - 1) / zc);
+    LAUNCH(c, (k_phaseA<T, VEC, PC, 1>), grid, dim3(32, 1), v, c->codes, zr, sold, snew,
+           P(c->q), c->sc, c->partials, par, zc);
   }
 
   // red-black IC(0): z = M^-1 r in two half sweeps; the red sweep also leaves
@@ -455,7 +475,10 @@ struct Impl {
         }
         const bool prof = c->profile_iters > 0 && it <= c->profile_iters;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1)], c->stream));
-        launch_phaseA<VEC, PC>(c, gridA, blockA, zr, P(sold), P(snew), par, zc);
+        if (g.nz == 1 && g.nzg == 1 && g.ny > 1 && !c->no_2d_view)
+          launch_phaseA_2d<VEC, PC>(c, zr, P(sold), P(snew), par);
+        else
+          launch_phaseA<VEC, PC>(c, gridA, blockA, zr, P(sold), P(snew), par, zc);
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 1], c->stream));
         if ((rc = gather_slots(c, c->sc->gA, 1))) return rc;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 2], c->stream));
@@ -685,6 +708,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   g.ncell = g.plane * d.nz;
   if (const char* e = getenv("SPL_ZCHUNK")) c->zchunk_override = atoi(e);
   if (const char* e = getenv("SPL_NO_RING")) c->no_ring = atoi(e) != 0;
+  if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
 
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));

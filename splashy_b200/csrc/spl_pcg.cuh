@@ -175,8 +175,11 @@ __device__ __forceinline__ void phaseA_scalars(Scal* sc, int par, int* stop_out,
 #ifndef SPL_PHASEA_MINB
 #define SPL_PHASEA_MINB 4     // resident CTAs per SM for fp32 (fp64: half)
 #endif
-template <typename T, int VEC, int PC>
-__global__ void __launch_bounds__(32 * TILE_Y, (sizeof(T) == 8) ? SPL_PHASEA_MINB / 2 : SPL_PHASEA_MINB)
+// TY = rows per CTA: 8 for 3-D boxes; 1 for the row-marching view of a 2-D box
+// (nz = 1 is presented as nx x 1 x ny, so the march runs along y and every warp is
+// independent -- the halo rows are outside the view and read as 0).
+template <typename T, int VEC, int PC, int TY>
+__global__ void __launch_bounds__(32 * TY, (TY == 1) ? 16 : ((sizeof(T) == 8) ? SPL_PHASEA_MINB / 2 : SPL_PHASEA_MINB))
 k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
          const T* __restrict__ sold, T* __restrict__ snew, T* __restrict__ q,
          Scal* __restrict__ sc, double* __restrict__ partials, int par, int zchunk) {
@@ -184,7 +187,7 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
   __shared__ double s_beta;
   __shared__ int s_stop;
   __shared__ T lut[8];
-  __shared__ VecT<T, VEC> tile[3][TILE_Y + 2][32];
+  __shared__ VecT<T, VEC> tile[3][TY + 2][32];
   const int tid = threadIdx.x + threadIdx.y * 32;
   fill_inv_lut<T>(lut);
   if (tid == 0) phaseA_scalars(sc, par, &s_stop, &s_beta);
@@ -194,7 +197,7 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
   const DirLoader<T, VEC, PC> dl{codes, zr, sold, snew, lut, g.nz, T(s_beta)};
   const int lane = threadIdx.x, ty = threadIdx.y;
   const int i0 = (blockIdx.x * 32 + lane) * VEC;
-  const int j = blockIdx.y * TILE_Y + ty;
+  const int j = blockIdx.y * TY + ty;
   const bool active = (i0 < g.nx) && (j < g.ny);
   const int kb = blockIdx.z * zchunk;
   const int ke = min(kb + zchunk, g.nz);
@@ -203,9 +206,9 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
   // neighbour owned by the adjacent CTA.  Rows / columns outside the box must
   // read as 0 (the Laplacian is unmasked, see lap_cell).
   const int hrow_j = (ty == 0) ? j - 1 : j + 1;
-  const bool hrow_ok = active && (ty == 0 || ty == TILE_Y - 1) && hrow_j >= 0 && hrow_j < g.ny;
+  const bool hrow_ok = (TY > 1) && active && (ty == 0 || ty == TY - 1) && hrow_j >= 0 && hrow_j < g.ny;
   const long long hoff = (ty == 0) ? -row : row;
-  const int hslot = (ty == 0) ? 0 : TILE_Y + 1;
+  const int hslot = (ty == 0) ? 0 : TY + 1;
   const bool has_e = active && ((lane == 0 && i0 > 0) || (lane == 31 && i0 + VEC < g.nx));
   const long long eoff = (lane == 0) ? -1 : VEC;
 
@@ -217,7 +220,7 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
   for (int b = 0; b < 3; ++b) {
     if (!active) tile[b][ty + 1][lane] = zero;                            // own row
     if (ty == 0 && !hrow_ok) tile[b][0][lane] = zero;                     // row j-1
-    if (ty == TILE_Y - 1 && !hrow_ok) tile[b][TILE_Y + 1][lane] = zero;   // row j+1
+    if (ty == TY - 1 && !hrow_ok) tile[b][TY + 1][lane] = zero;           // row j+1
   }
 
   double acc = 0.0;
@@ -305,7 +308,7 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
   if (tid == 0) partials[linear_block()] = bs;
   if (last_block(&sc->ticketA, nb)) {
     double t = 0.0;
-    for (unsigned b = tid; b < nb; b += 32 * TILE_Y) t += __ldcg(partials + b);
+    for (unsigned b = tid; b < nb; b += 32 * TY) t += __ldcg(partials + b);
     t = block_sum(t, red);
     if (tid == 0) sc->gA[sc->rank] = t;
   }
@@ -320,7 +323,7 @@ k_phaseA(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ zr,
 // them after cp.async.wait_group, so registers hold just the three combined
 // planes.  The slots are thread-private: no extra barrier is needed.
 #ifndef SPL_RING_D
-#define SPL_RING_D 5
+#define SPL_RING_D 4      // 4 stages x 3 CTAs/SM measured best (profiles/README.md)
 #endif
 constexpr int RING_D = SPL_RING_D;
 

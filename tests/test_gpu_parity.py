@@ -422,6 +422,44 @@ def test_cfg3_dambreak_256_converges_and_is_divergence_free():
     print("cfg3 iterations:", info["iters"], "ms_solve:", info["ms_solve"])
 
 
+def test_cfg2_smoke2d_4096_project_is_divergence_free():
+    """BASELINE config 2 at full size: 4096 x 4096 x 1 Taylor-Green + noise, PCG to 1e-6."""
+    sc = scenes.smoke2d(4096, dtype=np.float32)
+    lab, U, V, W = fields(sc, np.float32)
+    with solver_for(sc, dtype=np.float32, tol=1e-6, max_iters=60000) as s:
+        s.upload(lab, U, V, W)
+        s.advect(sc["dt"])
+        info = s.project(sc["dt"])
+        assert info["converged"] == 1 and info["nonfinite"] == 0
+        assert info["r_inf"] <= 1e-6 * info["b_inf"]
+        assert info["max_abs_div"] <= 1e-4 * vscale(U, V)
+    print("cfg2 iterations:", info["iters"], "ms_solve:", info["ms_solve"])
+
+
+def test_cfg4_vortex_512_slab_step_properties():
+    """BASELINE config 4 size (512^2 x 64 planes of it to keep the test short): the
+    residual falls monotonically enough, nothing escapes, fixed-iteration runs are
+    reproducible bit for bit."""
+    sc = scenes.vortex(512, 512, 64, dtype=np.float32)
+    lab, U, V, W = fields(sc, np.float32)
+    with solver_for(sc, dtype=np.float32, tol=1e-6) as s:
+        s.upload(lab, U, V, W)
+        s.snapshot()
+        s.set_fixed_iters(100)
+        a = s.step(sc["dt"])
+        pa = s.download()["P"]
+        s.restore()
+        b = s.step(sc["dt"])
+        pb = s.download()["P"]
+        assert a["trace_escapes"] == 0 and a["nonfinite"] == 0
+        assert a["r_inf"] < 0.5 * a["b_inf"]
+        assert np.array_equal(pa, pb)
+        s.set_fixed_iters(0)
+        s.restore()
+        c = s.step(sc["dt"])
+        assert c["converged"] == 1 and c["max_abs_div"] <= 1e-4 * vscale(U, V, W)
+
+
 def test_cfg2_smoke2d_4096_advect_properties():
     n = 4096
     lab = np.full((1, n, n), sr.FLUID, dtype=np.uint8)
