@@ -116,6 +116,8 @@ struct spl_ctx {
   double* partials = nullptr;  // 2 * MAX_PARTIALS
   int* flag = nullptr;         // device int (quirk "too far")
   int* hflag = nullptr;        // pinned
+  int* hdone = nullptr;        // pinned [2]: lagged convergence poll
+  cudaEvent_t dev[2]{};
   ncclComm_t comm = nullptr;
   bool uploaded = false, have_rhs = false, have_snapshot = false;
   int fixed_iters = 0;
@@ -459,6 +461,7 @@ struct Impl {
     const int limit = c->fixed_iters > 0 ? c->fixed_iters : c->d.max_iters;
     int it = 0;
     int nflush = 0;
+    int batch = 0;
     bool done = false;
     const int poll = 16;
     while (it < limit && !done) {
@@ -497,11 +500,18 @@ struct Impl {
         }
       }
       CU(cudaGetLastError());
-      if (c->fixed_iters > 0 && it < limit) continue;
-      CU(cudaMemcpyAsync(&c->hsc->done, &c->sc->done, sizeof(int), cudaMemcpyDeviceToHost,
+      if (c->fixed_iters > 0) continue;
+      // lagged poll: the flag of batch b is read while batch b+1 is already queued, so
+      // the GPU never waits for the host (a converged solve only runs no-op launches)
+      const int slot = batch & 1;
+      CU(cudaMemcpyAsync(&c->hdone[slot], &c->sc->done, sizeof(int), cudaMemcpyDeviceToHost,
                          c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      done = c->hsc->done != 0;
+      CU(cudaEventRecord(c->dev[slot], c->stream));
+      if (batch >= 1) {
+        CU(cudaEventSynchronize(c->dev[slot ^ 1]));
+        done = c->hdone[slot ^ 1] != 0;
+      }
+      ++batch;
     }
     // terms of the last (K mod m) iterations are still pending
     c->profile_flushes = nflush < 64 ? nflush : 64;
@@ -657,6 +667,9 @@ void spl_destroy(spl_ctx* c) {
   if (c->flag) cudaFree(c->flag);
   if (c->hsc) cudaFreeHost(c->hsc);
   if (c->hflag) cudaFreeHost(c->hflag);
+  if (c->hdone) cudaFreeHost(c->hdone);
+  for (cudaEvent_t e : c->dev)
+    if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev)
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->tev)
@@ -744,6 +757,8 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   CU(cudaMalloc(&c->flag, sizeof(int)));
   CU(cudaHostAlloc(&c->hsc, sizeof(Scal), cudaHostAllocDefault));
   CU(cudaHostAlloc(&c->hflag, sizeof(int), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&c->hdone, 2 * sizeof(int), cudaHostAllocDefault));
+  for (auto& e : c->dev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
   if (d.world > 1) {
     std::string err;
