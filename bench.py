@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="splashy_b200", choices=["splashy_b200", "reference"])
     ap.add_argument("--n", type=int, default=512, help="x = y = per-GPU z extent")
     ap.add_argument("--pcg-iters", type=int, default=200)
-    ap.add_argument("--precond", default="jacobi", choices=["none", "jacobi", "rbic0"])
+    ap.add_argument("--precond", default="jacobi", choices=["none", "jacobi", "rbic0", "mg"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tolerance-run", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the CPU sample box")

@@ -35,7 +35,7 @@ AIR, FLUID, SOLID, ABSENT = 0, 1, 2, 255
 # stencil-code bits (shared with splashy_b200/csrc/spl_common.cuh)
 B_XM, B_XP, B_YM, B_YP, B_ZM, B_ZP, B_FLUID = 1, 2, 4, 8, 16, 32, 64
 
-PC_NONE, PC_JACOBI, PC_RBIC0 = 0, 1, 2
+PC_NONE, PC_JACOBI, PC_RBIC0, PC_MG = 0, 1, 2, 3
 
 
 def _nb(a: np.ndarray, axis: int, d: int, fill=0) -> np.ndarray:
@@ -217,6 +217,79 @@ def apply_rbic0(codes: np.ndarray, E: np.ndarray, r: np.ndarray) -> np.ndarray:
     return z
 
 
+# ---- geometric multigrid V-cycle (splashy_b200/csrc/spl_mg.cuh) -----------------
+def mg_coarsen_labels(lab: np.ndarray) -> np.ndarray:
+    """Air if any child is Air, else Fluid if any child is Fluid, else Solid; children
+    outside the box (and absent cells) count as Solid."""
+    nz, ny, nx = lab.shape
+    cz, cy, cx = (nz + 1) // 2, (ny + 1) // 2, (nx + 1) // 2
+    pad = np.full((cz * 2, cy * 2, cx * 2), SOLID, dtype=np.uint8)
+    pad[:nz, :ny, :nx] = np.where(lab == ABSENT, SOLID, lab)
+    ch = pad.reshape(cz, 2, cy, 2, cx, 2).transpose(0, 2, 4, 1, 3, 5).reshape(cz, cy, cx, 8)
+    any_air = (ch == AIR).any(-1)
+    any_fl = (ch == FLUID).any(-1)
+    return np.where(any_air, AIR, np.where(any_fl, FLUID, SOLID)).astype(np.uint8)
+
+
+class Multigrid:
+    """V(nu, nu) cycle with damped Jacobi (omega = 2/3), 8-child average restriction,
+    piecewise-constant prolongation, rediscretised operators 4^-l * L_l and
+    `coarse_sweeps` Jacobi sweeps on the coarsest level (smallest extent <= 8)."""
+
+    def __init__(self, labels, nu: int = 2, coarse_sweeps: int = 30, dtype=np.float64,
+                 max_levels: int = 12):
+        self.nu, self.cs, self.dtype = nu, coarse_sweeps, np.dtype(dtype)
+        self.omega = self.dtype.type(2.0 / 3.0)
+        self.levels = []
+        lab, scale = labels, 1.0
+        while True:
+            codes = stencil_codes(lab)
+            fluid = (codes & B_FLUID) != 0
+            N = diag_count(codes)
+            w = np.where(fluid & (N > 0), self.omega / np.maximum(N, 1).astype(dtype), 0
+                         ).astype(dtype)
+            self.levels.append(dict(shape=lab.shape, codes=codes, fluid=fluid, w=w,
+                                    scale=self.dtype.type(scale),
+                                    inv_scale=self.dtype.type(1.0 / scale)))
+            dims = [d for d in lab.shape if d > 1]
+            if not dims or min(dims) <= 8 or len(self.levels) >= max_levels:
+                break
+            lab = mg_coarsen_labels(lab)
+            scale *= 0.25
+
+    def _lap(self, L, u):
+        """N u - sum of in-box non-solid neighbours (u = 0 on non-Fluid cells)."""
+        return apply_A(L["codes"], u)
+
+    def _smooth(self, L, u, b, sweeps, first):
+        for s in range(sweeps):
+            if first and s == 0:
+                u = L["w"] * (b * L["inv_scale"])
+            else:
+                u = u + L["w"] * (b * L["inv_scale"] - self._lap(L, u))
+            u = np.where(L["fluid"], u, 0).astype(self.dtype)
+        return u
+
+    def vcycle(self, b, lev: int = 0):
+        L = self.levels[lev]
+        b = np.where(L["fluid"], b, 0).astype(self.dtype)
+        last = lev == len(self.levels) - 1
+        if last:
+            sweeps = 2 * self.nu if len(self.levels) == 1 else self.cs
+            return self._smooth(L, None, b, sweeps, True)
+        u = self._smooth(L, None, b, self.nu, True)
+        r = np.where(L["fluid"], b - L["scale"] * self._lap(L, u), 0)
+        cz, cy, cx = self.levels[lev + 1]["shape"]
+        pad = np.zeros((cz * 2, cy * 2, cx * 2), dtype=self.dtype)
+        pad[:r.shape[0], :r.shape[1], :r.shape[2]] = r
+        rc = pad.reshape(cz, 2, cy, 2, cx, 2).sum(axis=(1, 3, 5)) * self.dtype.type(0.125)
+        ec = self.vcycle(rc.astype(self.dtype), lev + 1)
+        pe = np.repeat(np.repeat(np.repeat(ec, 2, 0), 2, 1), 2, 2)[:r.shape[0], :r.shape[1],
+                                                                  :r.shape[2]]
+        u = u + np.where(L["fluid"], pe, 0).astype(self.dtype)
+        return self._smooth(L, u, b, self.nu, False)
+
+
 def pcg(labels: np.ndarray, b: np.ndarray, precond: int = PC_JACOBI,
         tol: float = 1e-6, max_iters: int = 10000, tau: float = 0.0,
         dtype=np.float64, fixed_iters: Optional[int] = None
@@ -230,12 +303,15 @@ def pcg(labels: np.ndarray, b: np.ndarray, precond: int = PC_JACOBI,
     with np.errstate(divide="ignore"):
         invd = np.where(fluid & (N > 0), 1.0 / np.maximum(N, 1), 0.0).astype(dtype)
     E = rbic0_diag(codes, tau) if precond == PC_RBIC0 else None
+    mg = Multigrid(labels, dtype=dtype) if precond == PC_MG else None
 
     def M(r):
         if precond == PC_NONE:
             return r.copy()
         if precond == PC_JACOBI:
             return r * invd
+        if precond == PC_MG:
+            return mg.vcycle(r)
         return apply_rbic0(codes, E, r)
 
     def dot(a, c):

@@ -15,7 +15,7 @@ LIB_DIR = Path(__file__).resolve().parent / "lib"
 LIB_PATH = LIB_DIR / "libsplashy_cuda.so"
 
 SPL_F32, SPL_F64 = 0, 1
-SPL_PC_NONE, SPL_PC_JACOBI, SPL_PC_RBIC0 = 0, 1, 2
+SPL_PC_NONE, SPL_PC_JACOBI, SPL_PC_RBIC0, SPL_PC_MG = 0, 1, 2, 3
 SPL_AIR, SPL_FLUID, SPL_SOLID, SPL_ABSENT = 0, 1, 2, 255
 SPL_Q_REF_INTERP, SPL_Q_FORWARD_TRACE, SPL_Q_NEAREST_COPY = 1, 2, 4
 

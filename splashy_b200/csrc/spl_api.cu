@@ -19,11 +19,13 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <vector>
 #include <type_traits>
 
 #include "../../include/splashy_cuda.h"
 #include "spl_advect.cuh"
 #include "spl_common.cuh"
+#include "spl_mg.cuh"
 #include "spl_pcg.cuh"
 #include "spl_stencil.cuh"
 
@@ -88,6 +90,14 @@ thread_local std::string g_create_error;
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+struct MgLevel {
+  Geo g{};
+  uint8_t *media = nullptr, *codes = nullptr;   // plane-0 pointers
+  char *u = nullptr, *b = nullptr, *tmp = nullptr;
+  double scale = 1.0;                           // operator = scale * integer Laplacian
+  void* allocs[5]{};
+};
+
 struct spl_ctx {
   spl_desc d{};
   Geo g{};
@@ -121,6 +131,9 @@ struct spl_ctx {
   ncclComm_t comm = nullptr;
   bool uploaded = false, have_rhs = false, have_snapshot = false;
   int fixed_iters = 0;
+  std::vector<MgLevel> mg;     // SPL_PC_MG hierarchy; level 0 aliases codes / z / r / q
+  int mg_nu = 2;               // pre- and post-smoothing sweeps (SPL_MG_NU)
+  int mg_coarse = 30;          // sweeps on the coarsest level, even (SPL_MG_COARSE)
   int zchunk_override = 0;
   int ring_attr_set = 0;
   bool no_2d_view = false;     // SPL_NO_2D_VIEW=1: 2-D boxes use the 3-D tiling
@@ -397,7 +410,45 @@ struct Impl {
 
   // red-black IC(0): z = M^-1 r in two half sweeps; the red sweep also leaves
   // rho = r.z in slot `par`
+  // one multigrid V-cycle z = M^-1 r (spl_mg.cuh), then rho = r.z into slot `par`.
+  // Smoothing ping-pongs between u and tmp; the first sweep of a level writes tmp so
+  // that the result of its 2 nu sweeps (and of the even sweep count on the coarsest
+  // level) ends in u, i.e. in z on level 0.
+  static void vcycle(spl_ctx* c, int par) {
+    const int L = (int)c->mg.size();
+    const T omega = T(2.0 / 3.0);
+    auto smooth = [&](MgLevel& l, char*& cur, char*& oth, int first) {
+      LAUNCH(c, k_mg_smooth<T>, grid_for(c, l.g.ncell), 256, l.g, l.codes, P(cur), P(l.b),
+             P(oth), omega, T(1.0 / l.scale), first, c->sc);
+      std::swap(cur, oth);
+    };
+    std::vector<char*> cur(L), oth(L);
+    for (int l = 0; l < L; ++l) { cur[l] = c->mg[l].u; oth[l] = c->mg[l].tmp; }
+    for (int l = 0; l < L - 1; ++l) {
+      MgLevel& f = c->mg[l];
+      MgLevel& k = c->mg[l + 1];
+      for (int s = 0; s < c->mg_nu; ++s) smooth(f, cur[l], oth[l], s == 0);
+      LAUNCH(c, k_mg_restrict<T>, grid_for(c, k.g.ncell), 256, f.g, f.codes, P(cur[l]), P(f.b),
+             T(f.scale), k.g, k.codes, P(k.b), c->sc);
+    }
+    {
+      MgLevel& k = c->mg[L - 1];
+      const int sweeps = (L == 1) ? 2 * c->mg_nu : c->mg_coarse;
+      for (int s = 0; s < sweeps; ++s) smooth(k, cur[L - 1], oth[L - 1], s == 0);
+    }
+    for (int l = L - 2; l >= 0; --l) {
+      MgLevel& f = c->mg[l];
+      MgLevel& k = c->mg[l + 1];
+      LAUNCH(c, k_mg_prolong<T>, grid_for(c, f.g.ncell), 256, f.g, f.codes, P(cur[l]), k.g,
+             P(cur[l + 1]), c->sc);
+      for (int s = 0; s < c->mg_nu; ++s) smooth(f, cur[l], oth[l], 0);
+    }
+    LAUNCH(c, k_dot_rz<T>, grid_for(c, c->g.ncell), 256, c->g, P(c->r), P(c->z), c->sc,
+           c->partials, par);
+  }
+
   static void precondition(spl_ctx* c, int par) {
+    if (c->d.precond == SPL_PC_MG) { vcycle(c, par); return; }
     const Geo& g = c->g;
     const int grid = grid_for(c, g.ncell);
     LAUNCH(c, (k_rb_sweep<T, 1>), grid, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc,
@@ -447,12 +498,12 @@ struct Impl {
     const int zc = phaseA_zchunk(c, tx * ty);
     const dim3 gridA(tx, ty, (g.nz + zc - 1) / zc);
     const dim3 blockA(32, TILE_Y);
-    const T* zr = (PC == PC_RBIC0) ? P(c->z) : P(c->r);
+    const T* zr = pc_explicit_z(PC) ? P(c->z) : P(c->r);
 
     // rho_0 = r.z, max|b|  (phase B with alpha = 0)
     LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
            c->sc, c->partials, 0, 1, m);
-    if (PC == PC_RBIC0) precondition(c, 0);
+    if (pc_explicit_z(PC)) precondition(c, 0);
     int rc = gather_slots(c, &c->sc->gBM[0][0][0], 2);
     if (rc) return rc;
     LAUNCH(c, k_set_bmax, 1, 1, c->sc);
@@ -463,7 +514,7 @@ struct Impl {
     int nflush = 0;
     int batch = 0;
     bool done = false;
-    const int poll = 16;
+    const int poll = (PC == PC_MG) ? 1 : 16;   // an MG iteration is ~70 launches
     while (it < limit && !done) {
       const int stop = (it + poll < limit) ? it + poll : limit;
       for (; it < stop;) {
@@ -488,7 +539,7 @@ struct Impl {
         LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
                c->sc, c->partials, par, 0, m);
         if (prof) CU(cudaEventRecord(c->pev[3 * c->profile_iters + (it - 1)], c->stream));
-        if (PC == PC_RBIC0) precondition(c, par);   // z = M^-1 r, rho = r.z
+        if (pc_explicit_z(PC)) precondition(c, par);   // z = M^-1 r, rho = r.z
         if ((rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
         if (it % m == 0) {   // every buffer holds an unflushed direction: x += sum alpha s
           const bool pf = c->profile_iters > 0 && nflush < 64;
@@ -528,10 +579,12 @@ struct Impl {
       if (pc == SPL_PC_NONE) return pcg<4, PC_NONE>(c);
       if (pc == SPL_PC_JACOBI) return pcg<4, PC_JACOBI>(c);
       if (pc == SPL_PC_RBIC0) return pcg<4, PC_RBIC0>(c);
+      if (pc == SPL_PC_MG) return pcg<4, PC_MG>(c);
     } else {
       if (pc == SPL_PC_NONE) return pcg<1, PC_NONE>(c);
       if (pc == SPL_PC_JACOBI) return pcg<1, PC_JACOBI>(c);
       if (pc == SPL_PC_RBIC0) return pcg<1, PC_RBIC0>(c);
+      if (pc == SPL_PC_MG) return pcg<1, PC_MG>(c);
     }
     return fail(c, SPL_E_BADARG, "preconditioner %d is not available", pc);
   }
@@ -662,6 +715,9 @@ void spl_destroy(spl_ctx* c) {
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (void* p : c->alloc)
     if (p) cudaFree(p);
+  for (MgLevel& l : c->mg)
+    for (void* p : l.allocs)
+      if (p) cudaFree(p);
   if (c->sc) cudaFree(c->sc);
   if (c->partials) cudaFree(c->partials);
   if (c->flag) cudaFree(c->flag);
@@ -740,7 +796,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if (c->nsbuf > MAX_SBUF) c->nsbuf = MAX_SBUF;
   for (int i = 0; i < c->nsbuf; ++i)
     if ((rc = alloc_field(c, 16 + i, c->esz, &c->sbuf[i], 0))) return rc;
-  if (d.precond == SPL_PC_RBIC0) {
+  if (d.precond == SPL_PC_RBIC0 || d.precond == SPL_PC_MG) {
     if ((rc = alloc_field(c, 11, c->esz, &c->z, 0))) return rc;
     if ((rc = alloc_field(c, 12, c->esz, &c->einv, 0))) return rc;
   }
@@ -751,6 +807,44 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   c->codes = reinterpret_cast<uint8_t*>(tmp);
   if ((rc = alloc_field(c, 24, 1, &tmp, 0xFF))) return rc;   // BFS layers (spl_cleanup)
   c->layer = reinterpret_cast<uint8_t*>(tmp);
+  if (d.precond == SPL_PC_MG) {
+    if (d.world > 1)
+      return fail(c, SPL_E_BADARG, "SPL_PC_MG supports one GPU per box (world = 1) only");
+    if (const char* e = getenv("SPL_MG_NU")) c->mg_nu = atoi(e) > 0 ? atoi(e) : 2;
+    if (const char* e = getenv("SPL_MG_COARSE")) c->mg_coarse = atoi(e) > 1 ? atoi(e) & ~1 : 30;
+    // level 0 aliases the fine arrays; coarser levels until the smallest extent <= 8
+    MgLevel l0;
+    l0.g = c->g;
+    l0.media = c->media; l0.codes = c->codes;
+    l0.u = c->z; l0.b = c->r; l0.tmp = c->q;
+    c->mg.push_back(l0);
+    while ((int)c->mg.size() < MG_MAX_LEVELS) {
+      const Geo& f = c->mg.back().g;
+      int mind = 1 << 30;
+      if (f.nx > 1 && f.nx < mind) mind = f.nx;
+      if (f.ny > 1 && f.ny < mind) mind = f.ny;
+      if (f.nz > 1 && f.nz < mind) mind = f.nz;
+      if (mind <= 8 || mind == (1 << 30)) break;
+      MgLevel l;
+      l.g.nx = (f.nx + 1) / 2; l.g.ny = (f.ny + 1) / 2; l.g.nz = (f.nz + 1) / 2;
+      l.g.hz = 1; l.g.z0 = 0; l.g.nzg = l.g.nz;
+      l.g.plane = (long long)l.g.nx * l.g.ny;
+      l.g.ncell = l.g.plane * l.g.nz;
+      l.scale = c->mg.back().scale * 0.25;
+      const size_t cells = (size_t)l.g.plane * (l.g.nz + 2);
+      const size_t sizes[5] = {cells, cells, cells * c->esz, cells * c->esz, cells * c->esz};
+      char* base[5];
+      for (int a = 0; a < 5; ++a) {
+        CU(cudaMalloc(&l.allocs[a], sizes[a]));
+        CU(cudaMemsetAsync(l.allocs[a], a == 0 ? 0xFF : 0, sizes[a], c->stream));
+        base[a] = static_cast<char*>(l.allocs[a]) + (size_t)l.g.plane * (a < 2 ? 1 : c->esz);
+      }
+      l.media = reinterpret_cast<uint8_t*>(base[0]);
+      l.codes = reinterpret_cast<uint8_t*>(base[1]);
+      l.u = base[2]; l.b = base[3]; l.tmp = base[4];
+      c->mg.push_back(l);
+    }
+  }
   CU(cudaMalloc(&c->sc, sizeof(Scal)));
   CU(cudaMemsetAsync(c->sc, 0, sizeof(Scal), c->stream));
   CU(cudaMalloc(&c->partials, sizeof(double) * 2 * MAX_PARTIALS));
@@ -819,6 +913,13 @@ int spl_upload(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
   if (c->d.precond == SPL_PC_RBIC0) {
     rc = DISPATCH(c, Impl<float>::build_rbic0(c), Impl<double>::build_rbic0(c));
     if (rc) return rc;
+  }
+  for (size_t l = 1; l < c->mg.size(); ++l) {   // SPL_PC_MG: coarse labels and stencil codes
+    MgLevel& f = c->mg[l - 1];
+    MgLevel& k = c->mg[l];
+    LAUNCH(c, k_mg_coarsen, grid_for(c, k.g.ncell), 256, f.g, f.media, k.g, k.media);
+    LAUNCH(c, k_codes, grid_for(c, k.g.ncell), 256, k.g, k.media, k.codes);
+    CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(c->stream));
   c->uploaded = true;

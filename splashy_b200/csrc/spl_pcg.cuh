@@ -21,7 +21,10 @@
 
 namespace spl {
 
-enum { PC_NONE = 0, PC_JACOBI = 1, PC_RBIC0 = 2 };
+enum { PC_NONE = 0, PC_JACOBI = 1, PC_RBIC0 = 2, PC_MG = 3 };
+// preconditioners whose z = M^-1 r is a stored field produced by separate kernels
+// (phase A then reads z instead of r, phase B leaves rho = r.z to those kernels)
+__host__ __device__ constexpr bool pc_explicit_z(int pc) { return pc == PC_RBIC0 || pc == PC_MG; }
 
 // ---- scalar plumbing -------------------------------------------------------
 __device__ __forceinline__ double sum_slots(const double* g, int world, int stride = 1) {
@@ -677,7 +680,7 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
     m = block_max(m, red);
     if (tid == 0) {
       const int rank = sc->rank;
-      if (PC != PC_RBIC0) sc->gBM[par][rank][0] = t;
+      if (!pc_explicit_z(PC)) sc->gBM[par][rank][0] = t;
       sc->gBM[par][rank][1] = nanf ? kNaN : m;
       if (!init) sc->count = sc->count + 1;
     }

@@ -14,7 +14,7 @@ import numpy as np
 from . import _native as nat
 
 PRECOND = {"none": nat.SPL_PC_NONE, "jacobi": nat.SPL_PC_JACOBI,
-           "rbic0": nat.SPL_PC_RBIC0}
+           "rbic0": nat.SPL_PC_RBIC0, "mg": nat.SPL_PC_MG}
 
 
 class SplashyError(RuntimeError):

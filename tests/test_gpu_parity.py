@@ -155,6 +155,49 @@ def test_rbic0_iteration_count_matches_oracle_and_beats_jacobi(name, tau):
     assert info["max_abs_div"] <= 1e-6 * vscale(U, V, W)
 
 
+@pytest.mark.parametrize("name", sorted(SMALL_SCENES) + ["vortex64"])
+def test_multigrid_pcg_matches_oracle_and_direct_solve(name):
+    """SPL_PC_MG (opt-in): same V-cycle as oracle/dense_ref.Multigrid --
+    same iteration count -- and the converged pressure equals the direct solve."""
+    sc = (scenes.vortex(64, 64, 64, dtype=np.float64) if name == "vortex64"
+          else SMALL_SCENES[name](np.float64))
+    lab, U, V, W = fields(sc, np.float64)
+    with solver_for(sc, dtype=np.float64, tol=1e-9, precond="mg") as s:
+        s.upload(lab, U, V, W)
+        info = s.project(sc["dt"])
+        got = s.download()
+    with solver_for(sc, dtype=np.float64, tol=1e-9, precond="jacobi") as s:
+        s.upload(lab, U, V, W)
+        jinfo = s.project(sc["dt"])
+    b = dr.rhs(lab, U, V, W, sc["dt"], sc["h"], sc["rho"])
+    _, oinfo = dr.pcg(lab, b, dr.PC_MG, tol=1e-9)
+    assert abs(info["iters"] - oinfo["iters"]) <= 1, (info["iters"], oinfo["iters"])
+    assert info["iters"] < jinfo["iters"]
+    # exact answer: sparse LU on the small scenes; a 64^3 LU takes minutes, so the
+    # oracle's own MG-PCG at a tighter tolerance stands in there
+    big = name == "vortex64"
+    U2, V2, W2, P, _ = dr.project(lab, U, V, W, sc["dt"], sc["h"], sc["rho"], direct=not big,
+                                  precond=dr.PC_MG, tol=1e-12)
+    fl = lab == dr.FLUID
+    assert np.abs(got["P"][fl] - P[fl]).max() <= 1e-6 * vscale(P)
+    assert np.abs(got["U"] - U2).max() <= 1e-7 * vscale(U2, V2, W2)
+    assert info["max_abs_div"] <= 1e-7 * vscale(U, V, W)
+    print(name, "MG-PCG iterations", info["iters"], "Jacobi-PCG", jinfo["iters"])
+
+
+def test_multigrid_pcg_fp32_dambreak_128():
+    sc = scenes.dambreak(128, dtype=np.float32)
+    lab, U, V, W = fields(sc, np.float32)
+    res = {}
+    for pc in ("jacobi", "mg"):
+        with solver_for(sc, dtype=np.float32, tol=1e-6, precond=pc) as s:
+            s.upload(lab, U, V, W)
+            res[pc] = s.project(sc["dt"])
+    assert res["mg"]["converged"] == 1 and res["mg"]["iters"] * 8 < res["jacobi"]["iters"]
+    assert res["mg"]["max_abs_div"] <= 1e-4 * vscale(V)
+    print("dambreak128 iterations:", {k: (v["iters"], v["ms_solve"]) for k, v in res.items()})
+
+
 @pytest.mark.parametrize("name", sorted(SMALL_SCENES))
 def test_project_fp32_within_solver_tolerance(name):
     sc = SMALL_SCENES[name](np.float32)
