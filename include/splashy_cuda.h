@@ -176,6 +176,12 @@ int  spl_timer_stop(spl_ctx* ctx, float* ms);
  * is not modified (no gradient subtraction).                                   */
 int  spl_profile_pcg(spl_ctx* ctx, double dt, int iters, float* ms_phase_a,
                      float* ms_phase_b, float* ms_xflush);
+/* z = M^-1 r for the context's stored-z preconditioners (SPL_PC_RBIC0, SPL_PC_MG):
+ * r and z are host arrays of the box (nx*ny*nz, context dtype); the labels must
+ * have been uploaded.  One application of the operator PCG uses (parity tests
+ * against oracle/dense_ref.py apply_rbic0 / Multigrid.vcycle); also times it:
+ * *ms (nullable) receives the device time of the application.                  */
+int  spl_apply_preconditioner(spl_ctx* ctx, const void* r, void* z, float* ms);
 /* device pointer of a field including its z-halo (plumbing for tests):
  * which = 0 u,1 v,2 w,3 p,4 r,5 media,6 codes ; *halo_planes receives hz      */
 void* spl_device_ptr(spl_ctx* ctx, int which, int* halo_planes);

@@ -96,6 +96,7 @@ SYMBOLS = {
     "spl_profile_pcg": (C.c_int, [_VP, C.c_double, C.c_int, C.POINTER(C.c_float),
                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "spl_device_ptr": (_VP, [_VP, C.c_int, C.POINTER(C.c_int)]),
+    "spl_apply_preconditioner": (C.c_int, [_VP, _VP, _VP, C.POINTER(C.c_float)]),
 }
 
 _lib = None

@@ -27,6 +27,7 @@
 #include "spl_common.cuh"
 #include "spl_mg.cuh"
 #include "spl_pcg.cuh"
+#include "spl_mg_march.cuh"
 #include "spl_stencil.cuh"
 
 using namespace spl;
@@ -134,6 +135,8 @@ struct spl_ctx {
   std::vector<MgLevel> mg;     // SPL_PC_MG hierarchy; level 0 aliases codes / z / r / q
   int mg_nu = 2;               // pre- and post-smoothing sweeps (SPL_MG_NU)
   int mg_coarse = 30;          // sweeps on the coarsest level, even (SPL_MG_COARSE)
+  bool mg_no_march = false;    // SPL_MG_NO_MARCH=1: one-thread-per-cell kernels on every level
+  int mg_attr_set = 0;
   int zchunk_override = 0;
   int ring_attr_set = 0;
   bool no_2d_view = false;     // SPL_NO_2D_VIEW=1: 2-D boxes use the 3-D tiling
@@ -408,43 +411,144 @@ struct Impl {
            P(c->q), c->sc, c->partials, par, zc);
   }
 
-  // red-black IC(0): z = M^-1 r in two half sweeps; the red sweep also leaves
-  // rho = r.z in slot `par`
-  // one multigrid V-cycle z = M^-1 r (spl_mg.cuh), then rho = r.z into slot `par`.
-  // Smoothing ping-pongs between u and tmp; the first sweep of a level writes tmp so
-  // that the result of its 2 nu sweeps (and of the even sweep count on the coarsest
-  // level) ends in u, i.e. in z on level 0.
+  // ---- multigrid V-cycle z = M^-1 r, rho = r.z into slot `par` ------------------------
+  // A level runs the fused marching kernels (spl_mg_march.cuh) when it qualifies,
+  // otherwise the one-thread-per-cell kernels of spl_mg.cuh (same arithmetic).
+  static bool mg_fast(const spl_ctx* c, const MgLevel& l) {
+    return std::is_same<T, float>::value && !c->mg_no_march && l.g.nx % 4 == 0 &&
+           l.g.nx >= 64 && l.g.ny >= TILE_Y && l.g.nz >= 8;
+  }
+  static int mg_zchunk(const MgLevel& l) {
+    const int tiles = ((l.g.nx + 127) / 128) * ((l.g.ny + TILE_Y - 1) / TILE_Y);
+    const int gz = (2048 + tiles - 1) / tiles;
+    int zc = (l.g.nz + gz - 1) / gz;
+    if (zc < 8) zc = 8;
+    zc += zc & 1;                      // even: z pairs of the restriction stay inside a CTA
+    return zc;
+  }
+  template <int MODE, int OUT, int DOT>
+  static void mg_march(spl_ctx* c, const MgLevel& l, const char* a, char* out,
+                       const MgLevel* coarse, const char* ec, int par) {
+    if constexpr (std::is_same<T, float>::value) {
+      MgMarchArgs p{};
+      p.g = l.g;
+      p.codes = l.codes;
+      p.a = reinterpret_cast<const float*>(a);
+      p.b = reinterpret_cast<const float*>(l.b);
+      p.out = reinterpret_cast<float*>(out);
+      p.inv_scale = (float)(1.0 / l.scale);
+      p.scale = (float)l.scale;
+      p.omega = (float)(2.0 / 3.0);
+      if (coarse) {
+        p.ec = reinterpret_cast<const float*>(ec);
+        p.codes_c = coarse->codes;
+        p.bc = reinterpret_cast<float*>(coarse->b);
+        p.cnx = coarse->g.nx;
+        p.cny = coarse->g.ny;
+        p.cplane = coarse->g.plane;
+      }
+      p.sc = c->sc;
+      p.partials = c->partials;
+      p.par = par;
+      p.zchunk = mg_zchunk(l);
+      const dim3 grid((l.g.nx + 127) / 128, (l.g.ny + TILE_Y - 1) / TILE_Y,
+                      (l.g.nz + p.zchunk - 1) / p.zchunk);
+      using Smem = MgSmem<MODE, OUT>;
+      const int bit = 1 << (MODE * 4 + OUT * 2 + DOT);
+      if (!(c->mg_attr_set & bit)) {
+        cudaFuncSetAttribute(k_mg_march<MODE, OUT, DOT>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        c->mg_attr_set |= bit;
+      }
+      k_mg_march<MODE, OUT, DOT><<<grid, dim3(32, TILE_Y), sizeof(Smem), c->stream>>>(p);
+      c->launches++;
+    }
+  }
+
   static void vcycle(spl_ctx* c, int par) {
     const int L = (int)c->mg.size();
+    const int nu = c->mg_nu;
     const T omega = T(2.0 / 3.0);
-    auto smooth = [&](MgLevel& l, char*& cur, char*& oth, int first) {
-      LAUNCH(c, k_mg_smooth<T>, grid_for(c, l.g.ncell), 256, l.g, l.codes, P(cur), P(l.b),
-             P(oth), omega, T(1.0 / l.scale), first, c->sc);
-      std::swap(cur, oth);
+    std::vector<char*> cur(L, nullptr), nxt(L, nullptr);
+    auto other = [&](int l, char* b) { return b == c->mg[l].u ? c->mg[l].tmp : c->mg[l].u; };
+    auto simple_smooth = [&](int l, int first) {
+      MgLevel& v = c->mg[l];
+      LAUNCH(c, k_mg_smooth<T>, grid_for(c, v.g.ncell), 256, v.g, v.codes, P(cur[l]), P(v.b),
+             P(nxt[l]), omega, T(1.0 / v.scale), first, c->sc);
+      cur[l] = nxt[l];
+      nxt[l] = other(l, cur[l]);
     };
-    std::vector<char*> cur(L), oth(L);
-    for (int l = 0; l < L; ++l) { cur[l] = c->mg[l].u; oth[l] = c->mg[l].tmp; }
+    bool dot_done = false;
+    // `n` sweeps from a zero initial guess; `last` = the final launch of level 0
+    auto smooth_from_zero = [&](int l, int n, bool last) {
+      MgLevel& v = c->mg[l];
+      if (mg_fast(c, v) && n >= 2) {
+        const bool d0 = last && n == 2;
+        if (d0) mg_march<MG_FIRST2, MG_SMOOTH, 1>(c, v, v.b, nxt[l], nullptr, nullptr, par);
+        else mg_march<MG_FIRST2, MG_SMOOTH, 0>(c, v, v.b, nxt[l], nullptr, nullptr, par);
+        cur[l] = nxt[l];
+        nxt[l] = other(l, cur[l]);
+        for (int s = 2; s < n; ++s) {
+          const bool d = last && s == n - 1;
+          if (d) mg_march<MG_PLAIN, MG_SMOOTH, 1>(c, v, cur[l], nxt[l], nullptr, nullptr, par);
+          else mg_march<MG_PLAIN, MG_SMOOTH, 0>(c, v, cur[l], nxt[l], nullptr, nullptr, par);
+          cur[l] = nxt[l];
+          nxt[l] = other(l, cur[l]);
+        }
+        if (last) dot_done = true;
+      } else {
+        cur[l] = other(l, nxt[l]);       // not read by the first sweep
+        for (int s = 0; s < n; ++s) simple_smooth(l, s == 0);
+      }
+    };
+    // number of output alternations on a level that is not the coarsest, so that the
+    // result of the post-smoothing lands in u (= z on level 0)
+    for (int l = 0; l < L; ++l) {
+      MgLevel& v = c->mg[l];
+      int k;
+      if (l == L - 1) k = (L == 1) ? 2 * nu : c->mg_coarse;
+      else k = 2 * nu;
+      if (mg_fast(c, v) && ((l == L - 1) ? k >= 2 : nu >= 2)) k -= 1;   // FIRST2 = 2 sweeps
+      nxt[l] = (k & 1) ? v.u : v.tmp;
+    }
     for (int l = 0; l < L - 1; ++l) {
       MgLevel& f = c->mg[l];
       MgLevel& k = c->mg[l + 1];
-      for (int s = 0; s < c->mg_nu; ++s) smooth(f, cur[l], oth[l], s == 0);
-      LAUNCH(c, k_mg_restrict<T>, grid_for(c, k.g.ncell), 256, f.g, f.codes, P(cur[l]), P(f.b),
-             T(f.scale), k.g, k.codes, P(k.b), c->sc);
+      smooth_from_zero(l, nu, false);
+      if (mg_fast(c, f)) {
+        mg_march<MG_PLAIN, MG_RESTRICT, 0>(c, f, cur[l], nullptr, &k, nullptr, par);
+      } else {
+        LAUNCH(c, k_mg_restrict<T>, grid_for(c, k.g.ncell), 256, f.g, f.codes, P(cur[l]),
+               P(f.b), T(f.scale), k.g, k.codes, P(k.b), c->sc);
+      }
     }
-    {
-      MgLevel& k = c->mg[L - 1];
-      const int sweeps = (L == 1) ? 2 * c->mg_nu : c->mg_coarse;
-      for (int s = 0; s < sweeps; ++s) smooth(k, cur[L - 1], oth[L - 1], s == 0);
-    }
+    smooth_from_zero(L - 1, (L == 1) ? 2 * nu : c->mg_coarse, L == 1);
     for (int l = L - 2; l >= 0; --l) {
       MgLevel& f = c->mg[l];
       MgLevel& k = c->mg[l + 1];
-      LAUNCH(c, k_mg_prolong<T>, grid_for(c, f.g.ncell), 256, f.g, f.codes, P(cur[l]), k.g,
-             P(cur[l + 1]), c->sc);
-      for (int s = 0; s < c->mg_nu; ++s) smooth(f, cur[l], oth[l], 0);
+      if (mg_fast(c, f)) {
+        for (int s = 0; s < nu; ++s) {
+          const bool d = (l == 0) && s == nu - 1;
+          if (s == 0) {
+            if (d) mg_march<MG_PROLONG, MG_SMOOTH, 1>(c, f, cur[l], nxt[l], &k, cur[l + 1], par);
+            else mg_march<MG_PROLONG, MG_SMOOTH, 0>(c, f, cur[l], nxt[l], &k, cur[l + 1], par);
+          } else {
+            if (d) mg_march<MG_PLAIN, MG_SMOOTH, 1>(c, f, cur[l], nxt[l], nullptr, nullptr, par);
+            else mg_march<MG_PLAIN, MG_SMOOTH, 0>(c, f, cur[l], nxt[l], nullptr, nullptr, par);
+          }
+          cur[l] = nxt[l];
+          nxt[l] = other(l, cur[l]);
+        }
+        if (l == 0) dot_done = true;
+      } else {
+        LAUNCH(c, k_mg_prolong<T>, grid_for(c, f.g.ncell), 256, f.g, f.codes, P(cur[l]), k.g,
+               P(cur[l + 1]), c->sc);
+        for (int s = 0; s < nu; ++s) simple_smooth(l, 0);
+      }
     }
-    LAUNCH(c, k_dot_rz<T>, grid_for(c, c->g.ncell), 256, c->g, P(c->r), P(c->z), c->sc,
-           c->partials, par);
+    if (!dot_done)
+      LAUNCH(c, k_dot_rz<T>, grid_for(c, c->g.ncell), 256, c->g, P(c->r), P(c->z), c->sc,
+             c->partials, par);
   }
 
   static void precondition(spl_ctx* c, int par) {
@@ -811,6 +915,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
     if (d.world > 1)
       return fail(c, SPL_E_BADARG, "SPL_PC_MG supports one GPU per box (world = 1) only");
     if (const char* e = getenv("SPL_MG_NU")) c->mg_nu = atoi(e) > 0 ? atoi(e) : 2;
+    if (const char* e = getenv("SPL_MG_NO_MARCH")) c->mg_no_march = atoi(e) != 0;
     if (const char* e = getenv("SPL_MG_COARSE")) c->mg_coarse = atoi(e) > 1 ? atoi(e) & ~1 : 30;
     // level 0 aliases the fine arrays; coarser levels until the smallest extent <= 8
     MgLevel l0;
@@ -1207,6 +1312,31 @@ int spl_timer_stop(spl_ctx* c, float* ms) {
   CU(cudaEventRecord(c->tev[1], c->stream));
   CU(cudaEventSynchronize(c->tev[1]));
   CU(cudaEventElapsedTime(ms, c->tev[0], c->tev[1]));
+  return SPL_OK;
+}
+
+int spl_apply_preconditioner(spl_ctx* c, const void* r, void* z, float* ms) {
+  if (!c || !r || !z) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_apply_preconditioner before spl_upload");
+  if (c->d.precond != SPL_PC_RBIC0 && c->d.precond != SPL_PC_MG)
+    return fail(c, SPL_E_BADARG, "preconditioner %d has no stored z", c->d.precond);
+  if (c->d.world > 1) return fail(c, SPL_E_BADARG, "spl_apply_preconditioner needs world = 1");
+  CU(cudaSetDevice(c->d.device));
+  const size_t bytes = (size_t)c->g.ncell * c->esz;
+  CU(cudaMemcpyAsync(c->r, r, bytes, cudaMemcpyHostToDevice, c->stream));
+  Scal* h = c->hsc;
+  memset(h, 0, sizeof(Scal));
+  h->world = 1;
+  CU(cudaMemcpyAsync(c->sc, h, sizeof(Scal), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(c->tev[0], c->stream));
+  if (c->d.dtype == SPL_F64) Impl<double>::precondition(c, 0);
+  else Impl<float>::precondition(c, 0);
+  CU(cudaEventRecord(c->tev[1], c->stream));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(z, c->z, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (ms) CU(cudaEventElapsedTime(ms, c->tev[0], c->tev[1]));
+  c->have_rhs = false;      // r was overwritten
   return SPL_OK;
 }
 

@@ -223,6 +223,16 @@ class Solver:
                                               C.byref(b), C.byref(x)))
         return float(a.value), float(b.value), float(x.value)
 
+    def apply_preconditioner(self, r: np.ndarray):
+        """z = M^-1 r (SPL_PC_RBIC0 / SPL_PC_MG) for a host array of the box; returns
+        (z, device milliseconds of the application)."""
+        r = np.ascontiguousarray(r, dtype=self.dtype).reshape(self.shape)
+        z = np.empty_like(r)
+        ms = C.c_float()
+        self._check(self._lib.spl_apply_preconditioner(
+            self._ctx, C.c_void_p(r.ctypes.data), C.c_void_p(z.ctypes.data), C.byref(ms)))
+        return z, float(ms.value)
+
     def upload_ptrs(self, labels_ptr, u_ptr, v_ptr, w_ptr, p_ptr=None):
         """Raw host pointers (pinned buffers) -- no numpy conversion."""
         self._check(self._lib.spl_upload(self._ctx, labels_ptr, u_ptr, v_ptr,
