@@ -231,24 +231,36 @@ def mg_coarsen_labels(lab: np.ndarray) -> np.ndarray:
     return np.where(any_air, AIR, np.where(any_fl, FLUID, SOLID)).astype(np.uint8)
 
 
+def mg_weights(nu: int, omega: Optional[float] = None):
+    """Per-sweep damped-Jacobi weights: Chebyshev for eigenvalues of D^-1 A in [1/3, 2]
+    (the high-frequency band of the 7-point operator under 2x coarsening), ascending;
+    `omega` forces a constant weight instead."""
+    if omega is not None:
+        return [float(omega)] * nu
+    return [1.0 / (7.0 / 6.0 + 5.0 / 6.0 * np.cos(np.pi * (2 * k + 1) / (2.0 * nu)))
+            for k in range(nu)]
+
+
 class Multigrid:
-    """V(nu, nu) cycle with damped Jacobi (omega = 2/3), 8-child average restriction,
-    piecewise-constant prolongation, rediscretised operators 4^-l * L_l and
-    `coarse_sweeps` Jacobi sweeps on the coarsest level (smallest extent <= 8)."""
+    """V(nu, nu) cycle: damped Jacobi with the weights of `mg_weights` (pre-smoother in
+    ascending, post-smoother in descending order -- the cycle stays symmetric), 8-child
+    average restriction, piecewise-constant prolongation, rediscretised operators
+    4^-l * L_l and `coarse_sweeps` Jacobi sweeps on the coarsest level (smallest extent
+    <= 8).  Restates splashy_b200/csrc/spl_mg.cuh + spl_api.cu Impl::vcycle."""
 
     def __init__(self, labels, nu: int = 2, coarse_sweeps: int = 30, dtype=np.float64,
-                 max_levels: int = 12):
+                 max_levels: int = 12, omega: Optional[float] = None):
         self.nu, self.cs, self.dtype = nu, coarse_sweeps, np.dtype(dtype)
-        self.omega = self.dtype.type(2.0 / 3.0)
+        self.omegas = [self.dtype.type(w) for w in mg_weights(nu, omega)]
         self.levels = []
         lab, scale = labels, 1.0
         while True:
             codes = stencil_codes(lab)
             fluid = (codes & B_FLUID) != 0
             N = diag_count(codes)
-            w = np.where(fluid & (N > 0), self.omega / np.maximum(N, 1).astype(dtype), 0
-                         ).astype(dtype)
-            self.levels.append(dict(shape=lab.shape, codes=codes, fluid=fluid, w=w,
+            invn = np.where(fluid & (N > 0), 1.0 / np.maximum(N, 1).astype(dtype), 0
+                            ).astype(dtype)
+            self.levels.append(dict(shape=lab.shape, codes=codes, fluid=fluid, invn=invn,
                                     scale=self.dtype.type(scale),
                                     inv_scale=self.dtype.type(1.0 / scale)))
             dims = [d for d in lab.shape if d > 1]
@@ -261,12 +273,14 @@ class Multigrid:
         """N u - sum of in-box non-solid neighbours (u = 0 on non-Fluid cells)."""
         return apply_A(L["codes"], u)
 
-    def _smooth(self, L, u, b, sweeps, first):
+    def _smooth(self, L, u, b, sweeps, first, reverse=False):
         for s in range(sweeps):
+            k = s % self.nu
+            w = L["invn"] * self.omegas[self.nu - 1 - k if reverse else k]
             if first and s == 0:
-                u = L["w"] * (b * L["inv_scale"])
+                u = w * (b * L["inv_scale"])
             else:
-                u = u + L["w"] * (b * L["inv_scale"] - self._lap(L, u))
+                u = u + w * (b * L["inv_scale"] - self._lap(L, u))
             u = np.where(L["fluid"], u, 0).astype(self.dtype)
         return u
 
@@ -287,7 +301,7 @@ class Multigrid:
         pe = np.repeat(np.repeat(np.repeat(ec, 2, 0), 2, 1), 2, 2)[:r.shape[0], :r.shape[1],
                                                                   :r.shape[2]]
         u = u + np.where(L["fluid"], pe, 0).astype(self.dtype)
-        return self._smooth(L, u, b, self.nu, False)
+        return self._smooth(L, u, b, self.nu, False, reverse=True)
 
 
 def pcg(labels: np.ndarray, b: np.ndarray, precond: int = PC_JACOBI,

@@ -135,6 +135,8 @@ struct spl_ctx {
   std::vector<MgLevel> mg;     // SPL_PC_MG hierarchy; level 0 aliases codes / z / r / q
   int mg_nu = 2;               // pre- and post-smoothing sweeps (SPL_MG_NU)
   int mg_coarse = 30;          // sweeps on the coarsest level, even (SPL_MG_COARSE)
+  std::vector<double> mg_omega;  // per-sweep Jacobi weights: Chebyshev on [1/3, 2] (SPL_MG_OMEGA=w: constant)
+  bool mg_sumform = false;     // SPL_MG_SUMFORM=1: N s - sum Laplacian in the marching kernels
   bool mg_no_march = false;    // SPL_MG_NO_MARCH=1: one-thread-per-cell kernels on every level
   int mg_attr_set = 0;
   int zchunk_override = 0;
@@ -428,7 +430,8 @@ struct Impl {
   }
   template <int MODE, int OUT, int DOT>
   static void mg_march(spl_ctx* c, const MgLevel& l, const char* a, char* out,
-                       const MgLevel* coarse, const char* ec, int par) {
+                       const MgLevel* coarse, const char* ec, int par, double omega,
+                       double omega_v = 0.0) {
     if constexpr (std::is_same<T, float>::value) {
       MgMarchArgs p{};
       p.g = l.g;
@@ -438,7 +441,9 @@ struct Impl {
       p.out = reinterpret_cast<float*>(out);
       p.inv_scale = (float)(1.0 / l.scale);
       p.scale = (float)l.scale;
-      p.omega = (float)(2.0 / 3.0);
+      p.omega = (float)omega;
+      p.omega_v = (float)omega_v;
+      p.sumform = c->mg_sumform ? 1 : 0;
       if (coarse) {
         p.ec = reinterpret_cast<const float*>(ec);
         p.codes_c = coarse->codes;
@@ -468,41 +473,43 @@ struct Impl {
   static void vcycle(spl_ctx* c, int par) {
     const int L = (int)c->mg.size();
     const int nu = c->mg_nu;
-    const T omega = T(2.0 / 3.0);
+    const std::vector<double>& om = c->mg_omega;   // per-sweep weights (size nu)
     std::vector<char*> cur(L, nullptr), nxt(L, nullptr);
     auto other = [&](int l, char* b) { return b == c->mg[l].u ? c->mg[l].tmp : c->mg[l].u; };
-    auto simple_smooth = [&](int l, int first) {
-      MgLevel& v = c->mg[l];
-      LAUNCH(c, k_mg_smooth<T>, grid_for(c, v.g.ncell), 256, v.g, v.codes, P(cur[l]), P(v.b),
-             P(nxt[l]), omega, T(1.0 / v.scale), first, c->sc);
+    auto advance_buf = [&](int l) {
       cur[l] = nxt[l];
       nxt[l] = other(l, cur[l]);
     };
+    auto simple_smooth = [&](int l, int first, double omega) {
+      MgLevel& v = c->mg[l];
+      LAUNCH(c, k_mg_smooth<T>, grid_for(c, v.g.ncell), 256, v.g, v.codes, P(cur[l]), P(v.b),
+             P(nxt[l]), T(omega), T(1.0 / v.scale), first, c->sc);
+      advance_buf(l);
+    };
     bool dot_done = false;
-    // `n` sweeps from a zero initial guess; `last` = the final launch of level 0
+    // `n` sweeps from a zero initial guess, sweep s with weight om[s % nu];
+    // `last` = this ends with the final launch of level 0
     auto smooth_from_zero = [&](int l, int n, bool last) {
       MgLevel& v = c->mg[l];
       if (mg_fast(c, v) && n >= 2) {
         const bool d0 = last && n == 2;
-        if (d0) mg_march<MG_FIRST2, MG_SMOOTH, 1>(c, v, v.b, nxt[l], nullptr, nullptr, par);
-        else mg_march<MG_FIRST2, MG_SMOOTH, 0>(c, v, v.b, nxt[l], nullptr, nullptr, par);
-        cur[l] = nxt[l];
-        nxt[l] = other(l, cur[l]);
+        if (d0) mg_march<MG_FIRST2, MG_SMOOTH, 1>(c, v, v.b, nxt[l], nullptr, nullptr, par, om[1 % nu], om[0]);
+        else mg_march<MG_FIRST2, MG_SMOOTH, 0>(c, v, v.b, nxt[l], nullptr, nullptr, par, om[1 % nu], om[0]);
+        advance_buf(l);
         for (int s = 2; s < n; ++s) {
           const bool d = last && s == n - 1;
-          if (d) mg_march<MG_PLAIN, MG_SMOOTH, 1>(c, v, cur[l], nxt[l], nullptr, nullptr, par);
-          else mg_march<MG_PLAIN, MG_SMOOTH, 0>(c, v, cur[l], nxt[l], nullptr, nullptr, par);
-          cur[l] = nxt[l];
-          nxt[l] = other(l, cur[l]);
+          if (d) mg_march<MG_PLAIN, MG_SMOOTH, 1>(c, v, cur[l], nxt[l], nullptr, nullptr, par, om[s % nu]);
+          else mg_march<MG_PLAIN, MG_SMOOTH, 0>(c, v, cur[l], nxt[l], nullptr, nullptr, par, om[s % nu]);
+          advance_buf(l);
         }
         if (last) dot_done = true;
       } else {
         cur[l] = other(l, nxt[l]);       // not read by the first sweep
-        for (int s = 0; s < n; ++s) simple_smooth(l, s == 0);
+        for (int s = 0; s < n; ++s) simple_smooth(l, s == 0, om[s % nu]);
       }
     };
-    // number of output alternations on a level that is not the coarsest, so that the
-    // result of the post-smoothing lands in u (= z on level 0)
+    // first output buffer of every level, chosen so that the result of the
+    // post-smoothing lands in u (= z on level 0)
     for (int l = 0; l < L; ++l) {
       MgLevel& v = c->mg[l];
       int k;
@@ -516,34 +523,34 @@ struct Impl {
       MgLevel& k = c->mg[l + 1];
       smooth_from_zero(l, nu, false);
       if (mg_fast(c, f)) {
-        mg_march<MG_PLAIN, MG_RESTRICT, 0>(c, f, cur[l], nullptr, &k, nullptr, par);
+        mg_march<MG_PLAIN, MG_RESTRICT, 0>(c, f, cur[l], nullptr, &k, nullptr, par, 0.0);
       } else {
         LAUNCH(c, k_mg_restrict<T>, grid_for(c, k.g.ncell), 256, f.g, f.codes, P(cur[l]),
                P(f.b), T(f.scale), k.g, k.codes, P(k.b), c->sc);
       }
     }
     smooth_from_zero(L - 1, (L == 1) ? 2 * nu : c->mg_coarse, L == 1);
-    for (int l = L - 2; l >= 0; --l) {
+    for (int l = L - 2; l >= 0; --l) {      // post-smoothing: the weights in reverse order
       MgLevel& f = c->mg[l];
       MgLevel& k = c->mg[l + 1];
       if (mg_fast(c, f)) {
         for (int s = 0; s < nu; ++s) {
           const bool d = (l == 0) && s == nu - 1;
+          const double w = om[nu - 1 - s];
           if (s == 0) {
-            if (d) mg_march<MG_PROLONG, MG_SMOOTH, 1>(c, f, cur[l], nxt[l], &k, cur[l + 1], par);
-            else mg_march<MG_PROLONG, MG_SMOOTH, 0>(c, f, cur[l], nxt[l], &k, cur[l + 1], par);
+            if (d) mg_march<MG_PROLONG, MG_SMOOTH, 1>(c, f, cur[l], nxt[l], &k, cur[l + 1], par, w);
+            else mg_march<MG_PROLONG, MG_SMOOTH, 0>(c, f, cur[l], nxt[l], &k, cur[l + 1], par, w);
           } else {
-            if (d) mg_march<MG_PLAIN, MG_SMOOTH, 1>(c, f, cur[l], nxt[l], nullptr, nullptr, par);
-            else mg_march<MG_PLAIN, MG_SMOOTH, 0>(c, f, cur[l], nxt[l], nullptr, nullptr, par);
+            if (d) mg_march<MG_PLAIN, MG_SMOOTH, 1>(c, f, cur[l], nxt[l], nullptr, nullptr, par, w);
+            else mg_march<MG_PLAIN, MG_SMOOTH, 0>(c, f, cur[l], nxt[l], nullptr, nullptr, par, w);
           }
-          cur[l] = nxt[l];
-          nxt[l] = other(l, cur[l]);
+          advance_buf(l);
         }
         if (l == 0) dot_done = true;
       } else {
         LAUNCH(c, k_mg_prolong<T>, grid_for(c, f.g.ncell), 256, f.g, f.codes, P(cur[l]), k.g,
                P(cur[l + 1]), c->sc);
-        for (int s = 0; s < nu; ++s) simple_smooth(l, 0);
+        for (int s = 0; s < nu; ++s) simple_smooth(l, 0, om[nu - 1 - s]);
       }
     }
     if (!dot_done)
@@ -916,6 +923,16 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
       return fail(c, SPL_E_BADARG, "SPL_PC_MG supports one GPU per box (world = 1) only");
     if (const char* e = getenv("SPL_MG_NU")) c->mg_nu = atoi(e) > 0 ? atoi(e) : 2;
     if (const char* e = getenv("SPL_MG_NO_MARCH")) c->mg_no_march = atoi(e) != 0;
+    if (const char* e = getenv("SPL_MG_SUMFORM")) c->mg_sumform = atoi(e) != 0;
+    // Chebyshev weights for the eigenvalues of D^-1 A in [1/3, 2] (the high-frequency
+    // band of the 7-point operator under 2x coarsening), ascending; the post-smoother
+    // applies them in reverse, so the cycle stays symmetric.  oracle: dense_ref.mg_weights
+    c->mg_omega.assign(c->mg_nu, 2.0 / 3.0);
+    const char* ow = getenv("SPL_MG_OMEGA");
+    for (int k = 0; k < c->mg_nu; ++k) {
+      if (ow && atof(ow) > 0.0) c->mg_omega[k] = atof(ow);
+      else c->mg_omega[k] = 1.0 / (7.0 / 6.0 + 5.0 / 6.0 * cos(M_PI * (2 * k + 1) / (2.0 * c->mg_nu)));
+    }
     if (const char* e = getenv("SPL_MG_COARSE")) c->mg_coarse = atoi(e) > 1 ? atoi(e) & ~1 : 30;
     // level 0 aliases the fine arrays; coarser levels until the smallest extent <= 8
     MgLevel l0;

@@ -40,7 +40,10 @@ struct MgMarchArgs {
   const float* a;          // the field v is formed from: b (FIRST2) or u
   const float* b;          // right-hand side of the level (own cells only)
   float* out;              // smoothed field (MG_SMOOTH)
-  float inv_scale, scale, omega;
+  float inv_scale, scale;
+  float omega;             // weight of the sweep the epilogue performs
+  float omega_v;           // MG_FIRST2: weight of the first sweep (forms v)
+  int sumform;             // Laplacian as N s - sum (fewer instructions) instead of differences
   // coarse level (MG_PROLONG reads ec, MG_RESTRICT writes bc)
   const float* ec;
   const uint8_t* codes_c;
@@ -73,7 +76,8 @@ struct MgSmem {
   float4 tile[3][TILE_Y + 2][32];
   float2 rtile[OUT == MG_RESTRICT ? TILE_Y : 1][32];
   double red[32];
-  float wl[8];
+  float wl[8];      // omega / N
+  float wv[8];      // omega_v / N
 };
 
 template <int MODE, int OUT, int DOT>
@@ -85,9 +89,15 @@ k_mg_march(const MgMarchArgs p) {
   if (p.sc->done) return;
   const Geo& g = p.g;
   const int tid = threadIdx.x + threadIdx.y * 32;
-  if (tid < 8) sm_.wl[tid] = (tid >= 1 && tid <= 6) ? p.omega / float(tid) : 0.f;
+  if (tid < 8) {
+    sm_.wl[tid] = (tid >= 1 && tid <= 6) ? p.omega / float(tid) : 0.f;
+    sm_.wv[tid] = (tid >= 1 && tid <= 6) ? p.omega_v / float(tid) : 0.f;
+  }
   __syncthreads();
   const float* wl = sm_.wl;
+  const float* wv = sm_.wv;
+  const bool sumform = p.sumform != 0;
+  const float one_m_omega = 1.f - p.omega;
   const float inv_scale = p.inv_scale;
 
   const int lane = threadIdx.x, ty = threadIdx.y;
@@ -150,7 +160,7 @@ k_mg_march(const MgMarchArgs p) {
   };
   // v of one cell from its raw operand, code byte and parent correction
   auto vcell = [&](float a, unsigned code, float pe) {
-    if (MODE == MG_FIRST2) return wl[__popc(code & 63u)] * (a * inv_scale);
+    if (MODE == MG_FIRST2) return wv[__popc(code & 63u)] * (a * inv_scale);
     if (MODE == MG_PROLONG) return (code & (unsigned)B_FLUID) ? a + pe : 0.f;
     return a;
   };
@@ -268,12 +278,27 @@ k_mg_march(const MgMarchArgs p) {
         const unsigned code = (codec >> (8 * e)) & 0xffu;
         const float xm = (e > 0) ? s[e > 0 ? e - 1 : 0] : left;
         const float xp = (e < 3) ? s[e < 3 ? e + 1 : 0] : right;
-        const float lap = lap_cell<float>(code, s[e], xm, xp, ym[e], yp[e], zm[e], zp[e]);
+        const int n = __popc(code & 63u);
         if (OUT == MG_SMOOTH) {
-          const float w = wl[__popc(code & 63u)];
-          o[e] = (w != 0.f) ? s[e] + w * (bb[e] * inv_scale - lap) : 0.f;
+          const float w = wl[n];
+          float r;
+          if (sumform) {   // v + w (b' - N v + sum) = (1 - omega) v + w (b' + sum)
+            const float sum = ((xm + xp) + (ym[e] + yp[e])) + (zm[e] + zp[e]);
+            r = fmaf(w, fmaf(bb[e], inv_scale, sum), one_m_omega * s[e]);
+          } else {
+            const float lap = lap_cell<float>(code, s[e], xm, xp, ym[e], yp[e], zm[e], zp[e]);
+            r = s[e] + w * (bb[e] * inv_scale - lap);
+          }
+          o[e] = (w != 0.f) ? r : 0.f;
           if (DOT) part += bb[e] * o[e];
         } else {
+          float lap;
+          if (sumform) {
+            const float sum = ((xm + xp) + (ym[e] + yp[e])) + (zm[e] + zp[e]);
+            lap = fmaf(float(n), s[e], -sum);
+          } else {
+            lap = lap_cell<float>(code, s[e], xm, xp, ym[e], yp[e], zm[e], zp[e]);
+          }
           o[e] = (code & (unsigned)B_FLUID) ? bb[e] - p.scale * lap : 0.f;
         }
       }

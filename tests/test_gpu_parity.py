@@ -205,6 +205,8 @@ def _vcycle_case(shape, seed, solid_blob=True):
     ((64, 64, 128), np.float32, {"SPL_MG_NO_MARCH": "1"}),  # one-thread-per-cell kernels
     ((64, 64, 128), np.float32, {"SPL_MG_NU": "1"}),
     ((64, 64, 128), np.float32, {"SPL_MG_NU": "3"}),
+    ((64, 64, 128), np.float32, {"SPL_MG_SUMFORM": "1"}),  # N s - sum form of the stencil
+    ((64, 64, 128), np.float32, {"SPL_MG_OMEGA": "0.6666666666666666"}),
     ((33, 47, 61), np.float64, {}),
 ])
 def test_multigrid_vcycle_matches_oracle(shape, dtype, env, monkeypatch):
@@ -217,7 +219,9 @@ def test_multigrid_vcycle_matches_oracle(shape, dtype, env, monkeypatch):
         s.upload(lab, np.zeros(shape), np.zeros(shape), np.zeros(shape))
         z, ms = s.apply_preconditioner(r)
     nu = int(env.get("SPL_MG_NU", "2"))
-    ref = dr.Multigrid(lab, nu=nu, dtype=np.float64).vcycle(r.astype(dtype).astype(np.float64))
+    om = float(env["SPL_MG_OMEGA"]) if "SPL_MG_OMEGA" in env else None
+    ref = dr.Multigrid(lab, nu=nu, dtype=np.float64, omega=om).vcycle(
+        r.astype(dtype).astype(np.float64))
     tol = 2e-5 if dtype == np.float32 else 1e-12
     assert np.abs(z - ref).max() <= tol * vscale(ref), (np.abs(z - ref).max(), vscale(ref))
     assert np.all(z[lab != dr.FLUID] == 0)

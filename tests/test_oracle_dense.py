@@ -134,3 +134,40 @@ def test_scene_slabs_are_partition_invariant():
         part = scenes.vortex(12, 10, nz, z0=z0, nz_global=16)
         for k in ("labels", "U", "V", "W"):
             assert np.array_equal(part[k], whole[k][z0:z0 + nz])
+
+
+# --------------------------------------------------------------------------
+# multigrid preconditioner (oracle of SPL_PC_MG)
+# --------------------------------------------------------------------------
+def test_multigrid_vcycle_is_a_symmetric_positive_preconditioner():
+    rng = np.random.default_rng(11)
+    sc = scenes.dambreak(24, dtype=np.float64)
+    lab = sc["labels"]
+    fl = lab == dr.FLUID
+    for nu in (1, 2, 3):
+        mg = dr.Multigrid(lab, nu=nu)
+        x = np.where(fl, rng.uniform(-1, 1, lab.shape), 0.0)
+        y = np.where(fl, rng.uniform(-1, 1, lab.shape), 0.0)
+        mx, my = mg.vcycle(x), mg.vcycle(y)
+        assert abs((x * my).sum() - (mx * y).sum()) <= 1e-12 * abs((x * my).sum())
+        assert (x * mx).sum() > 0 and (y * my).sum() > 0
+        assert np.all(mx[~fl] == 0)
+
+
+def test_multigrid_pcg_converges_to_the_direct_solve_in_fewer_iterations():
+    sc = scenes.vortex(24, 20, 28, dtype=np.float64)
+    lab, U, V, W = sc["labels"], sc["U"], sc["V"], sc["W"]
+    b = dr.rhs(lab, U, V, W, sc["dt"], sc["h"], sc["rho"])
+    p_mg, i_mg = dr.pcg(lab, b, dr.PC_MG, tol=1e-10)
+    _, i_j = dr.pcg(lab, b, dr.PC_JACOBI, tol=1e-10)
+    p = dr.solve_direct(lab, b)
+    fl = lab == dr.FLUID
+    assert np.abs(p_mg[fl] - p[fl]).max() <= 1e-8 * np.abs(p).max()
+    assert i_mg["iters"] * 3 < i_j["iters"]
+
+
+def test_multigrid_chebyshev_weights():
+    w = dr.mg_weights(2)
+    assert abs(w[0] - 0.5695) < 1e-3 and abs(w[1] - 1.7321) < 1e-3
+    assert dr.mg_weights(1) == [6.0 / 7.0] or abs(dr.mg_weights(1)[0] - 6.0 / 7.0) < 1e-15
+    assert dr.mg_weights(3, omega=2.0 / 3.0) == [2.0 / 3.0] * 3
