@@ -137,6 +137,8 @@ struct spl_ctx {
   int mg_coarse = 30;          // sweeps on the coarsest level, even (SPL_MG_COARSE)
   std::vector<double> mg_omega;  // per-sweep Jacobi weights: Chebyshev on [1/3, 2] (SPL_MG_OMEGA=w: constant)
   bool mg_sumform = false;     // SPL_MG_SUMFORM=1: N s - sum Laplacian in the marching kernels
+  bool mg_no_bottom = false;   // SPL_MG_NO_BOTTOM=1: per-level launches down to the coarsest level
+  size_t mg_bottom_smem = 0;
   bool mg_no_march = false;    // SPL_MG_NO_MARCH=1: one-thread-per-cell kernels on every level
   int mg_attr_set = 0;
   int zchunk_override = 0;
@@ -518,7 +520,13 @@ struct Impl {
       if (mg_fast(c, v) && ((l == L - 1) ? k >= 2 : nu >= 2)) k -= 1;   // FIRST2 = 2 sweeps
       nxt[l] = (k & 1) ? v.u : v.tmp;
     }
-    for (int l = 0; l < L - 1; ++l) {
+    // levels [lb, L) fit one CTA's shared memory: a single launch runs their sub-cycle
+    int lb = L;
+    if (L >= 2 && !c->mg_no_bottom)
+      for (int l = 0; l < L; ++l)
+        if (c->mg[l].g.ncell <= MG_BOTTOM_CELLS && L - l <= MG_BOTTOM_LEVELS) { lb = l; break; }
+    const int ldown = lb < L ? lb : L - 1;   // levels [0, ldown) smooth + restrict
+    for (int l = 0; l < ldown; ++l) {
       MgLevel& f = c->mg[l];
       MgLevel& k = c->mg[l + 1];
       smooth_from_zero(l, nu, false);
@@ -529,8 +537,33 @@ struct Impl {
                P(f.b), T(f.scale), k.g, k.codes, P(k.b), c->sc);
       }
     }
-    smooth_from_zero(L - 1, (L == 1) ? 2 * nu : c->mg_coarse, L == 1);
-    for (int l = L - 2; l >= 0; --l) {      // post-smoothing: the weights in reverse order
+    if (lb < L) {
+      MgBottomArgs<T> a{};
+      a.nlev = L - lb;
+      a.nu = nu;
+      a.coarse_sweeps = c->mg_coarse;
+      for (int l = lb; l < L; ++l) {
+        a.g[l - lb] = c->mg[l].g;
+        a.codes[l - lb] = c->mg[l].codes;
+        a.scale[l - lb] = T(c->mg[l].scale);
+      }
+      for (int k = 0; k < nu; ++k) a.omega[k] = T(om[k]);
+      a.b0 = P(c->mg[lb].b);
+      a.u0 = P(c->mg[lb].u);
+      a.sc = c->sc;
+      const size_t smem = mg_bottom_smem<T>(a.g, a.nlev);
+      if (smem > c->mg_bottom_smem) {
+        cudaFuncSetAttribute(k_mg_bottom<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        c->mg_bottom_smem = smem;
+      }
+      k_mg_bottom<T><<<1, 1024, smem, c->stream>>>(a);
+      c->launches++;
+      cur[lb] = c->mg[lb].u;
+    } else {
+      smooth_from_zero(L - 1, (L == 1) ? 2 * nu : c->mg_coarse, L == 1);
+    }
+    for (int l = ldown - 1; l >= 0; --l) {      // post-smoothing: the weights in reverse order
       MgLevel& f = c->mg[l];
       MgLevel& k = c->mg[l + 1];
       if (mg_fast(c, f)) {
@@ -924,6 +957,8 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
     if (const char* e = getenv("SPL_MG_NU")) c->mg_nu = atoi(e) > 0 ? atoi(e) : 2;
     if (const char* e = getenv("SPL_MG_NO_MARCH")) c->mg_no_march = atoi(e) != 0;
     if (const char* e = getenv("SPL_MG_SUMFORM")) c->mg_sumform = atoi(e) != 0;
+    if (const char* e = getenv("SPL_MG_NO_BOTTOM")) c->mg_no_bottom = atoi(e) != 0;
+    if (c->mg_nu > MG_MAX_NU) c->mg_nu = MG_MAX_NU;
     // Chebyshev weights for the eigenvalues of D^-1 A in [1/3, 2] (the high-frequency
     // band of the 7-point operator under 2x coarsening), ascending; the post-smoother
     // applies them in reverse, so the cycle stays symmetric.  oracle: dense_ref.mg_weights

@@ -132,6 +132,143 @@ k_mg_prolong(Geo gf, const uint8_t* __restrict__ codes_f, T* __restrict__ u, Geo
   }
 }
 
+// ---- bottom of the V-cycle in one CTA ----------------------------------------------------
+// Levels with at most MG_BOTTOM_CELLS cells (16^3 and coarser) live entirely in shared
+// memory: the whole sub-cycle -- pre-smoothing, restriction, the coarsest-level sweeps,
+// prolongation, post-smoothing -- is one launch instead of ~35 launch-latency-bound ones.
+// Same arithmetic and order of operations as the per-level kernels above.
+constexpr int MG_BOTTOM_CELLS = 4096;
+constexpr int MG_BOTTOM_LEVELS = 4;
+constexpr int MG_MAX_NU = 8;
+
+template <typename T>
+struct MgBottomArgs {
+  int nlev, nu, coarse_sweeps;
+  Geo g[MG_BOTTOM_LEVELS];
+  const uint8_t* codes[MG_BOTTOM_LEVELS];
+  T scale[MG_BOTTOM_LEVELS];
+  T omega[MG_MAX_NU];
+  const T* b0;       // right-hand side of the first bottom level (global)
+  T* u0;             // its solution (global)
+  const Scal* sc;
+};
+
+template <typename T>
+__host__ __device__ inline size_t mg_bottom_smem(const Geo* g, int nlev) {
+  size_t bytes = 0;
+  for (int l = 0; l < nlev; ++l) {
+    const size_t n = (size_t)g[l].ncell;
+    bytes += 3 * ((n * sizeof(T) + 15) & ~size_t(15)) + ((n + 15) & ~size_t(15));
+  }
+  return bytes;
+}
+
+template <typename T>
+__device__ __forceinline__ T mg_lap_s(const Geo& g, unsigned c, int idx, const T* u, T u0) {
+  T sum = T(0);
+  if (c & B_XM) sum += u[idx - 1];
+  if (c & B_XP) sum += u[idx + 1];
+  if (c & B_YM) sum += u[idx - g.nx];
+  if (c & B_YP) sum += u[idx + g.nx];
+  if (c & B_ZM) sum += u[idx - (int)g.plane];
+  if (c & B_ZP) sum += u[idx + (int)g.plane];
+  return T(__popc(c & 63u)) * u0 - sum;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_mg_bottom(const MgBottomArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_bt[];
+  if (a.sc->done) return;
+  T* U[MG_BOTTOM_LEVELS];
+  T* V[MG_BOTTOM_LEVELS];
+  T* B[MG_BOTTOM_LEVELS];
+  uint8_t* C[MG_BOTTOM_LEVELS];
+  {
+    unsigned char* p = smem_bt;
+    for (int l = 0; l < a.nlev; ++l) {
+      const size_t n = (size_t)a.g[l].ncell;
+      const size_t fb = (n * sizeof(T) + 15) & ~size_t(15);
+      U[l] = reinterpret_cast<T*>(p); p += fb;
+      V[l] = reinterpret_cast<T*>(p); p += fb;
+      B[l] = reinterpret_cast<T*>(p); p += fb;
+      C[l] = p; p += (n + 15) & ~size_t(15);
+    }
+  }
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int l = 0; l < a.nlev; ++l)
+    for (int i = tid; i < (int)a.g[l].ncell; i += nt) C[l][i] = a.codes[l][i];
+  for (int i = tid; i < (int)a.g[0].ncell; i += nt) B[0][i] = a.b0[i];
+  __syncthreads();
+
+  // `sweeps` damped-Jacobi sweeps on level l; from zero when `first`; weights in
+  // ascending order, or descending (`rev`) for the post-smoother.  Result in U[l].
+  auto smooth = [&](int l, int sweeps, bool first, bool rev) {
+    const Geo& g = a.g[l];
+    const T inv_scale = T(1) / a.scale[l];
+    for (int s = 0; s < sweeps; ++s) {
+      const int k = s % a.nu;
+      const T omega = a.omega[rev ? a.nu - 1 - k : k];
+      const T* in = U[l];
+      T* out = V[l];
+      for (int i = tid; i < (int)g.ncell; i += nt) {
+        const unsigned c = C[l][i];
+        const int n = __popc(c & 63u);
+        T o = T(0);
+        if ((c & B_FLUID) && n > 0) {
+          const T w = omega / T(n);
+          if (first && s == 0) {
+            o = w * (B[l][i] * inv_scale);
+          } else {
+            const T u0 = in[i];
+            o = u0 + w * (B[l][i] * inv_scale - mg_lap_s<T>(g, c, i, in, u0));
+          }
+        }
+        out[i] = o;
+      }
+      __syncthreads();
+      T* t = U[l]; U[l] = V[l]; V[l] = t;
+    }
+  };
+
+  for (int l = 0; l + 1 < a.nlev; ++l) {
+    smooth(l, a.nu, true, false);
+    const Geo& gf = a.g[l];
+    const Geo& gc = a.g[l + 1];
+    for (int idx = tid; idx < (int)gc.ncell; idx += nt) {
+      T acc = T(0);
+      if (C[l + 1][idx] & B_FLUID) {
+        const int i = idx % gc.nx, t = idx / gc.nx, j = t % gc.ny, k = t / gc.ny;
+        for (int ch = 0; ch < 8; ++ch) {
+          const int fi = 2 * i + (ch & 1), fj = 2 * j + ((ch >> 1) & 1), fk = 2 * k + (ch >> 2);
+          if (fi < gf.nx && fj < gf.ny && fk < gf.nz) {
+            const int f = (fk * gf.ny + fj) * gf.nx + fi;
+            const unsigned cf = C[l][f];
+            if (cf & B_FLUID) acc += B[l][f] - a.scale[l] * mg_lap_s<T>(gf, cf, f, U[l], U[l][f]);
+          }
+        }
+        acc *= T(0.125);
+      }
+      B[l + 1][idx] = acc;
+    }
+    __syncthreads();
+  }
+  smooth(a.nlev - 1, a.coarse_sweeps, true, false);
+  for (int l = a.nlev - 2; l >= 0; --l) {
+    const Geo& gf = a.g[l];
+    const Geo& gc = a.g[l + 1];
+    for (int idx = tid; idx < (int)gf.ncell; idx += nt) {
+      if (C[l][idx] & B_FLUID) {
+        const int i = idx % gf.nx, t = idx / gf.nx, j = t % gf.ny, k = t / gf.ny;
+        U[l][idx] += U[l + 1][((k >> 1) * gc.ny + (j >> 1)) * gc.nx + (i >> 1)];
+      }
+    }
+    __syncthreads();
+    smooth(l, a.nu, false, true);
+  }
+  for (int i = tid; i < (int)a.g[0].ncell; i += nt) a.u0[i] = U[0][i];
+}
+
 // rho = r . z into the PCG slot (deterministic last-CTA reduction)
 template <typename T>
 __global__ void __launch_bounds__(256)

@@ -206,6 +206,8 @@ def _vcycle_case(shape, seed, solid_blob=True):
     ((64, 64, 128), np.float32, {"SPL_MG_NU": "1"}),
     ((64, 64, 128), np.float32, {"SPL_MG_NU": "3"}),
     ((64, 64, 128), np.float32, {"SPL_MG_SUMFORM": "1"}),  # N s - sum form of the stencil
+    ((64, 64, 128), np.float32, {"SPL_MG_NO_BOTTOM": "1"}),  # per-level launches to the coarsest
+    ((33, 47, 61), np.float64, {"SPL_MG_NO_BOTTOM": "1"}),
     ((64, 64, 128), np.float32, {"SPL_MG_OMEGA": "0.6666666666666666"}),
     ((33, 47, 61), np.float64, {}),
 ])
