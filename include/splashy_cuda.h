@@ -47,7 +47,14 @@ enum { SPL_AIR = 0, SPL_FLUID = 1, SPL_SOLID = 2, SPL_ABSENT = 255 };
 enum {
   SPL_Q_REF_INTERP    = 1u << 0, /* Convection.fs:35,42-47 offsets + int-snap key */
   SPL_Q_FORWARD_TRACE = 1u << 1, /* Convection.fs:54,56 sign                       */
-  SPL_Q_NEAREST_COPY  = 1u << 2  /* Convection.fs:57,63-64 whole-vector copy       */
+  SPL_Q_NEAREST_COPY  = 1u << 2, /* Convection.fs:57,63-64 whole-vector copy       */
+  /* marker stage, literal readings of Simulator.fs / Grid.fs / Build.fs */
+  SPL_Q_MARKER_SUM    = 1u << 3, /* Simulator.fs:24-35 marker velocity = SUM of the two
+                                    faces (intended: their mean)                    */
+  SPL_Q_MOVE_CELLS    = 1u << 4, /* Grid.fs:42-47 the cell record travels with its
+                                    marker, the old coordinate is deleted           */
+  SPL_Q_LAZY_BUFFER   = 1u << 5  /* Build.fs:83-86 air buffer grows from cells that
+                                    existed before the call only (one ring per step) */
 };
 
 /* return codes; text from spl_last_error mirrors the reference's failwith   */
@@ -59,7 +66,9 @@ enum {
   SPL_E_NONFINITE     = -4,  /* Vector.fs:17 / Pressure.fs:138-142                  */
   SPL_E_DIVERGENCE    = -5,  /* Pressure.fs:149 "Velocity field is not correct"     */
   SPL_E_NOT_CONVERGED = -6,  /* PCG hit max_iters (no reference counterpart)        */
-  SPL_E_STATE         = -7   /* call order (e.g. project before upload)             */
+  SPL_E_STATE         = -7,  /* call order (e.g. project before upload)             */
+  SPL_E_MARKER        = -8   /* Build.fs:162-174 "Fluid marker went outside bounds" /
+                                "does not have a neighbor"; marker left the dense box */
 };
 
 /* ---- descriptor (replaces the [<Literal>]s of Constants.fs:10-36) -------- */
@@ -141,6 +150,8 @@ int  spl_cleanup(spl_ctx* ctx);
  * viscosity, project (+ checks with the reference's 1e-4 threshold when
  * `sanity` != 0), cleanup                                                      */
 int  spl_advance(spl_ctx* ctx, double dt, int sanity, spl_info* info);
+/* (when markers are set, spl_advance starts with spl_move_markers + spl_relabel:
+ * the whole of Simulator.advance, Simulator.fs:54-110)                         */
 /* Pressure.divergence over every Fluid cell (Pressure.fs:16-32) -> kept on the
  * device as the PCG right-hand side b = (h rho/dt) * div (Pressure.fs:64-68) */
 int  spl_divergence(spl_ctx* ctx, double dt, spl_info* info);
@@ -157,6 +168,27 @@ int  spl_step(spl_ctx* ctx, double dt, spl_info* info);
 /* page-locked host buffers for the upload / download calls                   */
 void* spl_host_alloc(size_t bytes);
 void  spl_host_free(void* p);
+/* ---- marker stage: the step before the path ---------------------
+ * Simulator.fs:19-52,60-79.  Markers are fp64 locations in metres held on the device;
+ * cell of a location = Coord.construct(float) (Coord.fs:49-67) minus desc.origin.
+ * world = 1 only.                                                               */
+/* World.contains (World.fs:11-14, Aabb.fs:13-17) as inclusive box-index bounds; cells
+ * created outside become Solid (Build.fs:95-98).  Default: the whole box.          */
+int  spl_set_world(spl_ctx* ctx, const int lo[3], const int hi[3]);
+/* Simulator.generate's state: n marker locations, xyz = n x 3 doubles (metres)     */
+int  spl_set_markers(spl_ctx* ctx, int64_t n, const double* xyz);
+int  spl_get_markers(spl_ctx* ctx, double* xyz);          /* n x 3 doubles out      */
+/* Simulator.move_markers (+ Grid.move_cells under SPL_Q_MOVE_CELLS): every location
+ * advances by dt * velocity of its cell; *moved = markers that changed cell.       */
+int  spl_move_markers(spl_ctx* ctx, double dt, int64_t* moved);
+/* Build.setup block of Simulator.advance (:66-75): Fluid = cells holding a marker,
+ * air buffer of Build.max_distance = 2 rings, everything else deleted; rebuilds the
+ * stencil codes / preconditioner.  sanity != 0 adds Build.check_containment and
+ * Build.check_surroundings (-> SPL_E_MARKER with the reference's message).         */
+int  spl_relabel(spl_ctx* ctx, int sanity);
+/* current cell labels (nx*ny*nz bytes: SPL_AIR / FLUID / SOLID / ABSENT)           */
+int  spl_download_media(spl_ctx* ctx, uint8_t* media);
+
 /* keep a copy of the current u,v,w on the device / restore it (lets a bench
  * repeat the same step without a host round trip)                            */
 int  spl_snapshot(spl_ctx* ctx);

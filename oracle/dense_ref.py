@@ -626,3 +626,119 @@ def cleanup(labels, U, V, W):
     """Simulator.fs:100-110 (Build.cleanup): propagate, zero into-solid, zero solids."""
     U, V, W = propagate_velocities(labels, U, V, W)
     return zero_solid_velocities(labels, U, V, W)
+
+
+# --------------------------------------------------------------------------
+# "next" row N3 of SURVEY 8f: marker motion + cell relabelling (the step before the path)
+# --------------------------------------------------------------------------
+def nearest_cell_index(x: np.ndarray, h: float = 10.0) -> np.ndarray:
+    """Coord.construct(float) (Coord.fs:49-67) as a world cell index: round half even to an
+    integer (metres), then snap to the multiple of h with the .NET remainder rule (ties of
+    +-h/2 go up for positive, towards zero for negative coordinates)."""
+    hi = int(h)
+    n = np.rint(np.asarray(x, dtype=np.float64)).astype(np.int64)
+    r = np.fmod(n, hi)                                   # sign of the dividend
+    snapped = np.where(r == 0, n, np.where(r >= hi // 2, n + (hi - r), n - r))
+    return (snapped // hi).astype(np.int64)
+
+
+def marker_cells(loc: np.ndarray, h: float, origin) -> np.ndarray:
+    """(n, 3) box indices (i, j, k) of the cells the marker locations (metres) snap to."""
+    idx = nearest_cell_index(loc, h)
+    return idx - np.asarray(origin, dtype=np.int64)[None, :]
+
+
+def marker_velocity(labels, U, V, W, cells: np.ndarray, sum_faces: bool = False) -> np.ndarray:
+    """Simulator.get_velocity (Simulator.fs:24-35): the cell's +face velocity plus the
+    -neighbours' components on the shared faces (absent neighbour: 0).  The reference adds
+    the two faces (`sum_faces`, quirk); intended = their mean, the cell-centre velocity."""
+    nz, ny, nx = labels.shape
+    out = np.zeros((len(cells), 3))
+    for a, F in enumerate((U, V, W)):
+        i, j, k = cells[:, 0], cells[:, 1], cells[:, 2]
+        own = F[k, j, i].astype(np.float64)
+        bi, bj, bk = i - (a == 0), j - (a == 1), k - (a == 2)
+        ok = (bi >= 0) & (bj >= 0) & (bk >= 0)
+        back = np.where(ok, F[np.maximum(bk, 0), np.maximum(bj, 0),
+                              np.maximum(bi, 0)].astype(np.float64), 0.0)
+        back = np.where(ok & (labels[np.maximum(bk, 0), np.maximum(bj, 0),
+                                     np.maximum(bi, 0)] != ABSENT), back, 0.0)
+        out[:, a] = own + back if sum_faces else 0.5 * (own + back)
+    return out
+
+
+def move_markers(labels, U, V, W, loc, dt, h, origin, sum_faces: bool = False):
+    """Simulator.move_markers (Simulator.fs:38-52): loc += dt * velocity(cell(loc)).
+    Returns (new locations, old cells, new cells) -- cells as box indices (i, j, k)."""
+    loc = np.asarray(loc, dtype=np.float64)
+    old = marker_cells(loc, h, origin)
+    v = marker_velocity(labels, U, V, W, old, sum_faces)
+    new_loc = loc + v * dt
+    return new_loc, old, marker_cells(new_loc, h, origin)
+
+
+def relabel(labels, U, V, W, P, cells, world_lo, world_hi, max_distance: int = 2,
+            lazy_buffer: bool = False):
+    """Build.setup block of Simulator.advance (Simulator.fs:66-75, Build.fs:37-102) on
+    the dense box: Fluid = in-world, non-Solid cells holding a marker (a Fluid cell without
+    one turns into Air, velocity kept); BFS layers 1..max_distance grow from the non-solid
+    cells of the previous layer through every neighbour -- an absent neighbour is created
+    as Air (inside the world) or Solid (outside), zero velocity / pressure; cells that get
+    no layer are deleted (ABSENT, zeroed).  `lazy_buffer` = the reference's literal rule:
+    only cells that existed before this call act as BFS sources (Build.fs:83-86 reads the
+    grid before the additions are committed), so the buffer grows one ring per step.
+    `world_lo/hi`: inclusive box-index bounds of World.contains (Aabb.fs:13-17)."""
+    nz, ny, nx = labels.shape
+    kk, jj, ii = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    in_world = ((ii >= world_lo[0]) & (ii <= world_hi[0]) & (jj >= world_lo[1]) &
+                (jj <= world_hi[1]) & (kk >= world_lo[2]) & (kk <= world_hi[2]))
+    has_marker = np.zeros(labels.shape, dtype=bool)
+    c = np.asarray(cells, dtype=np.int64).reshape(-1, 3)
+    inside = ((c >= 0).all(1) & (c[:, 0] < nx) & (c[:, 1] < ny) & (c[:, 2] < nz))
+    has_marker[c[inside, 2], c[inside, 1], c[inside, 0]] = True
+    fluid = has_marker & in_world & (labels != SOLID)
+    lab = np.where(fluid, FLUID, np.where(labels == FLUID, AIR, labels)).astype(np.uint8)
+    existed = lab != ABSENT
+    layer = np.where(fluid, 0, -1).astype(np.int32)
+    for i in range(1, max_distance + 1):
+        src = (layer == i - 1) & (lab != SOLID) & (lab != ABSENT)
+        if lazy_buffer:
+            src &= existed
+        near = np.zeros(labels.shape, dtype=bool)
+        for axis in range(3):
+            for d in (-1, +1):
+                near |= _nb(src, axis, d, False)
+        take = near & (layer < 0) & (lab != FLUID)
+        created = take & (lab == ABSENT)
+        lab = np.where(created, np.where(in_world, AIR, SOLID), lab).astype(np.uint8)
+        layer = np.where(take, i, layer)
+    gone = layer < 0
+    lab = np.where(gone, ABSENT, lab).astype(np.uint8)
+    fresh = gone | ((labels == ABSENT) & ~gone)
+    out = [np.where(fresh, F.dtype.type(0), F) for F in (U, V, W)]
+    Pn = np.where(fresh | (lab == AIR), P.dtype.type(0), P)
+    return lab, out[0], out[1], out[2], Pn
+
+
+def move_cells(labels, U, V, W, P, old, new):
+    """Grid.move_cells (Grid.fs:42-47), the reference's literal rule (quirk): the whole
+    cell record -- media, velocity, pressure -- travels with its marker to the new
+    coordinate and the old coordinate is deleted.  `moved` is built by prepending
+    (Simulator.fs:45-50), i.e. processed in reverse marker order.  A target outside the
+    box cannot be represented: raises IndexError."""
+    lab = labels.copy()
+    F = [U.copy(), V.copy(), W.copy(), P.copy()]
+    pairs = [(tuple(o), tuple(n)) for o, n in zip(np.asarray(old), np.asarray(new))
+             if tuple(o) != tuple(n)]
+    nz, ny, nx = labels.shape
+    for (oi, oj, ok), (ni, nj, nk) in reversed(pairs):
+        if not (0 <= ni < nx and 0 <= nj < ny and 0 <= nk < nz):
+            raise IndexError("marker left the dense box")
+        if lab[ok, oj, oi] == ABSENT:                     # raw_get on a missing cell
+            raise KeyError("Grid.raw_get: no cell at the marker's old coordinate")
+        lab[nk, nj, ni] = lab[ok, oj, oi]
+        for A in F:
+            A[nk, nj, ni] = A[ok, oj, oi]
+            A[ok, oj, oi] = 0
+        lab[ok, oj, oi] = ABSENT
+    return lab, F[0], F[1], F[2], F[3]

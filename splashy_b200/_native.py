@@ -18,6 +18,8 @@ SPL_F32, SPL_F64 = 0, 1
 SPL_PC_NONE, SPL_PC_JACOBI, SPL_PC_RBIC0, SPL_PC_MG = 0, 1, 2, 3
 SPL_AIR, SPL_FLUID, SPL_SOLID, SPL_ABSENT = 0, 1, 2, 255
 SPL_Q_REF_INTERP, SPL_Q_FORWARD_TRACE, SPL_Q_NEAREST_COPY = 1, 2, 4
+SPL_Q_MARKER_SUM, SPL_Q_MOVE_CELLS, SPL_Q_LAZY_BUFFER = 8, 16, 32
+SPL_Q_ALL = 63
 
 SPL_OK = 0
 SPL_E_BADARG, SPL_E_CUDA, SPL_E_TRACE, SPL_E_NONFINITE = -1, -2, -3, -4
@@ -97,6 +99,12 @@ SYMBOLS = {
                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "spl_device_ptr": (_VP, [_VP, C.c_int, C.POINTER(C.c_int)]),
     "spl_apply_preconditioner": (C.c_int, [_VP, _VP, _VP, C.POINTER(C.c_float)]),
+    "spl_set_world": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "spl_set_markers": (C.c_int, [_VP, C.c_int64, _VP]),
+    "spl_get_markers": (C.c_int, [_VP, _VP]),
+    "spl_move_markers": (C.c_int, [_VP, C.c_double, C.POINTER(C.c_int64)]),
+    "spl_relabel": (C.c_int, [_VP, C.c_int]),
+    "spl_download_media": (C.c_int, [_VP, _VP]),
 }
 
 _lib = None

@@ -28,6 +28,7 @@
 #include "spl_mg.cuh"
 #include "spl_pcg.cuh"
 #include "spl_mg_march.cuh"
+#include "spl_markers.cuh"
 #include "spl_stencil.cuh"
 
 using namespace spl;
@@ -132,6 +133,13 @@ struct spl_ctx {
   ncclComm_t comm = nullptr;
   bool uploaded = false, have_rhs = false, have_snapshot = false;
   int fixed_iters = 0;
+  // marker stage
+  long long nmark = 0;
+  double* mloc = nullptr;      // nmark x 3 locations (metres)
+  long long *mold = nullptr, *mnew = nullptr;   // cells before / after the last move
+  uint8_t* mark = nullptr;     // per cell: holds a marker / existed before relabelling
+  MarkerStats* mstats = nullptr;   // device
+  WorldBox world{};            // World.contains as box indices
   std::vector<MgLevel> mg;     // SPL_PC_MG hierarchy; level 0 aliases codes / z / r / q
   int mg_nu = 2;               // pre- and post-smoothing sweeps (SPL_MG_NU)
   int mg_coarse = 30;          // sweeps on the coarsest level, even (SPL_MG_COARSE)
@@ -862,6 +870,11 @@ void spl_destroy(spl_ctx* c) {
   for (MgLevel& l : c->mg)
     for (void* p : l.allocs)
       if (p) cudaFree(p);
+  if (c->mloc) cudaFree(c->mloc);
+  if (c->mold) cudaFree(c->mold);
+  if (c->mnew) cudaFree(c->mnew);
+  if (c->mark) cudaFree(c->mark);
+  if (c->mstats) cudaFree(c->mstats);
   if (c->sc) cudaFree(c->sc);
   if (c->partials) cudaFree(c->partials);
   if (c->flag) cudaFree(c->flag);
@@ -1020,6 +1033,8 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
     NC(g_nccl.CommInitRank(&c->comm, d.world, id, d.rank));
   }
   c->d.nccl_id = nullptr;   // caller-owned bytes are not kept
+  for (int a = 0; a < 3; ++a) c->world.lo[a] = 0;
+  c->world.hi[0] = c->g.nx - 1; c->world.hi[1] = c->g.ny - 1; c->world.hi[2] = c->g.nz - 1;
   CU(cudaStreamSynchronize(c->stream));
   return SPL_OK;
 }
@@ -1036,6 +1051,26 @@ int spl_create(spl_ctx** out, const spl_desc* desc) {
     return rc;
   }
   *out = c;
+  return SPL_OK;
+}
+
+// everything derived from the labels: stencil codes, preconditioner data
+static int rebuild_operators(spl_ctx* c) {
+  const Geo& g = c->g;
+  int rc;
+  LAUNCH(c, k_codes, grid_for(c, g.ncell), 256, g, c->media, c->codes);
+  CU(cudaGetLastError());
+  if (c->d.precond == SPL_PC_RBIC0) {
+    rc = DISPATCH(c, Impl<float>::build_rbic0(c), Impl<double>::build_rbic0(c));
+    if (rc) return rc;
+  }
+  for (size_t l = 1; l < c->mg.size(); ++l) {   // SPL_PC_MG: coarse labels and stencil codes
+    MgLevel& f = c->mg[l - 1];
+    MgLevel& k = c->mg[l];
+    LAUNCH(c, k_mg_coarsen, grid_for(c, k.g.ncell), 256, f.g, f.media, k.g, k.media);
+    LAUNCH(c, k_codes, grid_for(c, k.g.ncell), 256, k.g, k.media, k.codes);
+    CU(cudaGetLastError());
+  }
   return SPL_OK;
 }
 
@@ -1065,19 +1100,7 @@ int spl_upload(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
   }
   int rc = exchange_halo(c, reinterpret_cast<char*>(c->media), 1, ncclUint8, g.hz);
   if (rc) return rc;
-  LAUNCH(c, k_codes, grid_for(c, g.ncell), 256, g, c->media, c->codes);
-  CU(cudaGetLastError());
-  if (c->d.precond == SPL_PC_RBIC0) {
-    rc = DISPATCH(c, Impl<float>::build_rbic0(c), Impl<double>::build_rbic0(c));
-    if (rc) return rc;
-  }
-  for (size_t l = 1; l < c->mg.size(); ++l) {   // SPL_PC_MG: coarse labels and stencil codes
-    MgLevel& f = c->mg[l - 1];
-    MgLevel& k = c->mg[l];
-    LAUNCH(c, k_mg_coarsen, grid_for(c, k.g.ncell), 256, f.g, f.media, k.g, k.media);
-    LAUNCH(c, k_codes, grid_for(c, k.g.ncell), 256, k.g, k.media, k.codes);
-    CU(cudaGetLastError());
-  }
+  if ((rc = rebuild_operators(c))) return rc;
   CU(cudaStreamSynchronize(c->stream));
   c->uploaded = true;
   c->have_rhs = false;
@@ -1251,15 +1274,170 @@ int spl_step(spl_ctx* c, double dt, spl_info* info) {
   return project_impl(c, dt, info, true);
 }
 
+// ---- marker stage ---------------------------------------------------------
+static int markers_need(spl_ctx* c, const char* who) {
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "%s before spl_upload", who);
+  if (c->nmark <= 0) return fail(c, SPL_E_STATE, "%s before spl_set_markers", who);
+  if (c->d.world > 1) return fail(c, SPL_E_BADARG, "the marker stage needs world = 1");
+  return SPL_OK;
+}
+
+static int read_marker_stats(spl_ctx* c, MarkerStats* out) {
+  CU(cudaMemcpyAsync(out, c->mstats, sizeof(MarkerStats), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
+}
+
+int spl_set_world(spl_ctx* c, const int lo[3], const int hi[3]) {
+  if (!c || !lo || !hi) return SPL_E_BADARG;
+  for (int a = 0; a < 3; ++a) {
+    c->world.lo[a] = lo[a];
+    c->world.hi[a] = hi[a];
+  }
+  return SPL_OK;
+}
+
+int spl_set_markers(spl_ctx* c, int64_t n, const double* xyz) {
+  if (!c || n < 0 || (n > 0 && !xyz)) return SPL_E_BADARG;
+  if (c->d.world > 1) return fail(c, SPL_E_BADARG, "the marker stage needs world = 1");
+  CU(cudaSetDevice(c->d.device));
+  if (c->mloc) { cudaFree(c->mloc); cudaFree(c->mold); cudaFree(c->mnew); }
+  c->mloc = nullptr; c->mold = c->mnew = nullptr;
+  c->nmark = n;
+  if (!c->mstats) CU(cudaMalloc(&c->mstats, sizeof(MarkerStats)));
+  if (!c->mark) CU(cudaMalloc(&c->mark, (size_t)c->g.ncell));
+  if (n == 0) return SPL_OK;
+  CU(cudaMalloc(&c->mloc, (size_t)n * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->mold, (size_t)n * sizeof(long long)));
+  CU(cudaMalloc(&c->mnew, (size_t)n * sizeof(long long)));
+  CU(cudaMemcpyAsync(c->mloc, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                     c->stream));
+  CU(cudaMemsetAsync(c->mstats, 0, sizeof(MarkerStats), c->stream));
+  LAUNCH(c, k_marker_cells, grid_for(c, n), 256, c->g, c->mloc, (long long)n, (int)c->d.h,
+         c->d.origin[0], c->d.origin[1], c->d.origin[2], c->mnew, c->mstats);
+  CU(cudaMemcpyAsync(c->mold, c->mnew, (size_t)n * sizeof(long long), cudaMemcpyDeviceToDevice,
+                     c->stream));
+  MarkerStats st;
+  int rc = read_marker_stats(c, &st);
+  if (rc) return rc;
+  if (st.outside)
+    return fail(c, SPL_E_MARKER, "%llu marker(s) lie outside the dense box", st.outside);
+  return SPL_OK;
+}
+
+int spl_get_markers(spl_ctx* c, double* xyz) {
+  if (!c || !xyz) return SPL_E_BADARG;
+  if (c->nmark <= 0) return fail(c, SPL_E_STATE, "spl_get_markers before spl_set_markers");
+  CU(cudaSetDevice(c->d.device));
+  CU(cudaMemcpyAsync(xyz, c->mloc, (size_t)c->nmark * 3 * sizeof(double),
+                     cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
+}
+
+int spl_move_markers(spl_ctx* c, double dt, int64_t* moved) {
+  if (!c) return SPL_E_BADARG;
+  int rc = markers_need(c, "spl_move_markers");
+  if (rc) return rc;
+  CU(cudaSetDevice(c->d.device));
+  const long long n = c->nmark;
+  const int sum_faces = (c->d.quirks & SPL_Q_MARKER_SUM) ? 1 : 0;
+  CU(cudaMemsetAsync(c->mstats, 0, sizeof(MarkerStats), c->stream));
+  if (c->d.dtype == SPL_F64) {
+    LAUNCH(c, k_move_markers<double>, grid_for(c, n), 256, c->g, c->media,
+           Impl<double>::P(c->u), Impl<double>::P(c->v), Impl<double>::P(c->w), c->mloc, n, dt,
+           (int)c->d.h, c->d.origin[0], c->d.origin[1], c->d.origin[2], sum_faces, c->mold,
+           c->mnew, c->mstats);
+  } else {
+    LAUNCH(c, k_move_markers<float>, grid_for(c, n), 256, c->g, c->media, Impl<float>::P(c->u),
+           Impl<float>::P(c->v), Impl<float>::P(c->w), c->mloc, n, dt, (int)c->d.h,
+           c->d.origin[0], c->d.origin[1], c->d.origin[2], sum_faces, c->mold, c->mnew,
+           c->mstats);
+  }
+  CU(cudaGetLastError());
+  MarkerStats st;
+  if ((rc = read_marker_stats(c, &st))) return rc;
+  if (moved) *moved = (int64_t)st.moved;
+  if (st.outside)   // Grid.raw_get on a coordinate the box cannot hold
+    return fail(c, SPL_E_MARKER, "%llu marker(s) left the dense box", st.outside);
+  if ((c->d.quirks & SPL_Q_MOVE_CELLS) && st.moved) {
+    double* p = reinterpret_cast<double*>(c->p);
+    if (c->d.dtype == SPL_F64)
+      LAUNCH(c, k_move_records<double>, grid_for(c, n), 256, c->g, c->media,
+             Impl<double>::P(c->u), Impl<double>::P(c->v), Impl<double>::P(c->w), p, c->mold,
+             c->mnew, n);
+    else
+      LAUNCH(c, k_move_records<float>, grid_for(c, n), 256, c->g, c->media, Impl<float>::P(c->u),
+             Impl<float>::P(c->v), Impl<float>::P(c->w), p, c->mold, c->mnew, n);
+    CU(cudaGetLastError());
+    c->have_rhs = false;
+  }
+  return SPL_OK;
+}
+
+int spl_relabel(spl_ctx* c, int sanity) {
+  if (!c) return SPL_E_BADARG;
+  int rc = markers_need(c, "spl_relabel");
+  if (rc) return rc;
+  CU(cudaSetDevice(c->d.device));
+  const Geo& g = c->g;
+  const int grid = grid_for(c, g.ncell);
+  const int lazy = (c->d.quirks & SPL_Q_LAZY_BUFFER) ? 1 : 0;
+  CU(cudaMemsetAsync(c->mark, 0, (size_t)g.ncell, c->stream));
+  CU(cudaMemsetAsync(c->mstats, 0, sizeof(MarkerStats), c->stream));
+  LAUNCH(c, k_mark_cells, grid_for(c, c->nmark), 256, c->mnew, c->nmark, c->mark);
+  LAUNCH(c, k_relabel_init, grid, 256, g, c->world, c->media, c->layer, c->mark, c->mstats);
+  for (int step = 1; step <= 2; ++step)   // Build.max_distance = max 2 (ceil time_step_constant)
+    LAUNCH(c, k_relabel_step, grid, 256, g, c->world, c->media, c->layer, c->mark, step, lazy);
+  double* p = reinterpret_cast<double*>(c->p);
+  if (c->d.dtype == SPL_F64)
+    LAUNCH(c, k_relabel_finish<double>, grid, 256, g, c->media, c->layer, c->mark,
+           Impl<double>::P(c->u), Impl<double>::P(c->v), Impl<double>::P(c->w), p);
+  else
+    LAUNCH(c, k_relabel_finish<float>, grid, 256, g, c->media, c->layer, c->mark,
+           Impl<float>::P(c->u), Impl<float>::P(c->v), Impl<float>::P(c->w), p);
+  CU(cudaGetLastError());
+  if ((rc = rebuild_operators(c))) return rc;
+  c->have_rhs = false;
+  MarkerStats st;
+  if (sanity) {
+    unsigned long long* missing = &c->mstats->moved;   // reuse: zero since the memset above
+    LAUNCH(c, k_check_surroundings, grid_for(c, c->nmark), 256, g, c->media, c->mnew, c->nmark,
+           missing);
+  }
+  if ((rc = read_marker_stats(c, &st))) return rc;
+  if (sanity && st.escaped)      // Build.fs:162-166
+    return fail(c, SPL_E_MARKER, "Error: Fluid marker went outside bounds (%llu marker cells).",
+                st.escaped);
+  if (sanity && st.moved)        // Build.fs:168-174
+    return fail(c, SPL_E_MARKER, "Fluid marker does not have a neighbor. (%llu markers)",
+                st.moved);
+  return SPL_OK;
+}
+
+int spl_download_media(spl_ctx* c, uint8_t* media) {
+  if (!c || !media) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_download_media before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  CU(cudaMemcpyAsync(media, c->media, (size_t)c->g.ncell, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
+}
+
 int spl_advance(spl_ctx* c, double dt, int sanity, spl_info* info) {
   if (!c) return SPL_E_BADARG;
   if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_advance before spl_upload");
   if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
   CU(cudaSetDevice(c->d.device));
+  int rc = SPL_OK;
+  if (c->nmark > 0) {   // Simulator.fs:60-79: move markers, rebuild the cell labels
+    if ((rc = spl_move_markers(c, dt, nullptr))) return rc;
+    if ((rc = spl_relabel(c, sanity))) return rc;
+  }
   // Simulator.fs:82-86: convection, forces, viscosity (advect's error checks need the
   // escape counter, so it goes through the public entry point)
   spl_info adv;
-  int rc = spl_advect(c, dt, &adv);
+  rc = spl_advect(c, dt, &adv);
   if (rc) return rc;
   if ((rc = DISPATCH(c, Impl<float>::forces(c, dt), Impl<double>::forces(c, dt)))) return rc;
   if ((rc = DISPATCH(c, Impl<float>::viscosity(c, dt), Impl<double>::viscosity(c, dt)))) return rc;

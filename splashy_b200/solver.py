@@ -223,6 +223,36 @@ class Solver:
                                               C.byref(b), C.byref(x)))
         return float(a.value), float(b.value), float(x.value)
 
+    # -- marker stage (Simulator.fs:19-52,60-79) ---------------------------
+    def set_world(self, lo: Sequence[int], hi: Sequence[int]) -> None:
+        """World.contains as inclusive box-index bounds (i, j, k)."""
+        a = (C.c_int * 3)(*lo)
+        b = (C.c_int * 3)(*hi)
+        self._check(self._lib.spl_set_world(self._ctx, a, b))
+
+    def set_markers(self, xyz: np.ndarray) -> None:
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        self._nmark = len(xyz)
+        self._check(self._lib.spl_set_markers(self._ctx, len(xyz), C.c_void_p(xyz.ctypes.data)))
+
+    def get_markers(self) -> np.ndarray:
+        out = np.empty((self._nmark, 3), dtype=np.float64)
+        self._check(self._lib.spl_get_markers(self._ctx, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def move_markers(self, dt: float) -> int:
+        moved = C.c_int64()
+        self._check(self._lib.spl_move_markers(self._ctx, dt, C.byref(moved)))
+        return int(moved.value)
+
+    def relabel(self, sanity: bool = True) -> None:
+        self._check(self._lib.spl_relabel(self._ctx, 1 if sanity else 0))
+
+    def download_media(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=np.uint8)
+        self._check(self._lib.spl_download_media(self._ctx, C.c_void_p(out.ctypes.data)))
+        return out
+
     def apply_preconditioner(self, r: np.ndarray):
         """z = M^-1 r (SPL_PC_RBIC0 / SPL_PC_MG) for a host array of the box; returns
         (z, device milliseconds of the application)."""
