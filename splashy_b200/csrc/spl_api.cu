@@ -153,6 +153,7 @@ struct spl_ctx {
   int ring_attr_set = 0;
   bool no_2d_view = false;     // SPL_NO_2D_VIEW=1: 2-D boxes use the 3-D tiling
   bool no_ring = false;        // SPL_NO_RING=1: force the generic phase-A kernel
+  bool no_quad = false;        // SPL_NO_QUAD=1: one-cell-per-thread div / grad / check kernels
   int64_t launches = 0;
   double rhs_dt = 0.0;
   std::string err;
@@ -375,6 +376,14 @@ struct Impl {
     const Geo& g = c->g;
     int rc = exchange_velocity(c, 1);
     if (rc) return rc;
+    if constexpr (std::is_same<T, float>::value) {
+      if (g.nx % 4 == 0 && !c->no_quad) {
+        LAUNCH(c, k_div_rhs4, grid_for(c, g.ncell / 4), 256, g, c->codes, P(c->u), P(c->v),
+               P(c->w), P(out), scale);
+        CU(cudaGetLastError());
+        return SPL_OK;
+      }
+    }
     LAUNCH(c, k_div_rhs<T>, grid_for(c, g.ncell), 256, g, c->codes, P(c->u), P(c->v),
            P(c->w), P(out), scale);
     CU(cudaGetLastError());
@@ -746,6 +755,14 @@ struct Impl {
     int rc = exchange_halo(c, c->p, 8, ncclDouble, 1);
     if (rc) return rc;
     const double kappa = dt / (c->d.h * c->d.rho);
+    if constexpr (std::is_same<T, float>::value) {
+      if (g.nx % 4 == 0 && !c->no_quad) {
+        LAUNCH(c, k_grad_sub4, grid_for(c, g.ncell / 4), 256, g, c->media,
+               reinterpret_cast<const double*>(c->p), P(c->u), P(c->v), P(c->w), kappa);
+        CU(cudaGetLastError());
+        return SPL_OK;
+      }
+    }
     LAUNCH(c, k_grad_sub<T>, grid_for(c, g.ncell), 256, g, c->media,
            reinterpret_cast<const double*>(c->p), P(c->u),
            P(c->v), P(c->w), kappa);
@@ -757,8 +774,16 @@ struct Impl {
     const Geo& g = c->g;
     int rc = exchange_velocity(c, 1);
     if (rc) return rc;
-    LAUNCH(c, k_check<T>, grid_for(c, g.ncell), 256, g, c->codes, P(c->u), P(c->v), P(c->w),
-           reinterpret_cast<const double*>(c->p), c->sc, c->partials);
+    bool quad = false;
+    if constexpr (std::is_same<T, float>::value) quad = g.nx % 4 == 0 && !c->no_quad;
+    if constexpr (std::is_same<T, float>::value) {
+      if (quad)
+        LAUNCH(c, k_check4, grid_for(c, g.ncell / 4), 256, g, c->codes, P(c->u), P(c->v),
+               P(c->w), reinterpret_cast<const double*>(c->p), c->sc, c->partials);
+    }
+    if (!quad)
+      LAUNCH(c, k_check<T>, grid_for(c, g.ncell), 256, g, c->codes, P(c->u), P(c->v), P(c->w),
+             reinterpret_cast<const double*>(c->p), c->sc, c->partials);
     CU(cudaGetLastError());
     return gather_slots(c, c->sc->gD, 1);
   }
@@ -934,6 +959,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   g.ncell = g.plane * d.nz;
   if (const char* e = getenv("SPL_ZCHUNK")) c->zchunk_override = atoi(e);
   if (const char* e = getenv("SPL_NO_RING")) c->no_ring = atoi(e) != 0;
+  if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
 
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

@@ -145,6 +145,183 @@ k_check(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ u,
   }
 }
 
+// ---- 4-cells-per-thread variants (fp32, nx % 4 = 0) -----------------------------------
+// Same arithmetic, cell by cell, as k_div_rhs / k_grad_sub / k_check; a thread owns 4
+// consecutive x cells: 128-bit accesses for the own cells and the -y / -z (+y / +z)
+// neighbours, one scalar for the x neighbour outside the quad, one div / mod per quad.
+// Every neighbour address stays inside the allocation (z-halo planes exist), validity
+// comes from the code bits / the labels.
+__device__ __forceinline__ float quad_div(unsigned c, float u0, float um, float v0, float vm,
+                                          float w0, float wm) {
+  const float ox = (c & B_XP) ? u0 : 0.f;
+  const float oy = (c & B_YP) ? v0 : 0.f;
+  const float oz = (c & B_ZP) ? w0 : 0.f;
+  const float ix = (c & B_XM) ? um : 0.f;
+  const float iy = (c & B_YM) ? vm : 0.f;
+  const float iz = (c & B_ZM) ? wm : 0.f;
+  return ((ix - ox) + (iy - oy)) + (iz - oz);
+}
+
+__global__ void __launch_bounds__(256)
+k_div_rhs4(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ u,
+           const float* __restrict__ v, const float* __restrict__ w, float* __restrict__ out,
+           float scale) {
+  const long long nq = g.ncell >> 2;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq;
+       q += (long long)gridDim.x * blockDim.x) {
+    const long long idx = q << 2;
+    const unsigned c4 = *reinterpret_cast<const unsigned*>(codes + idx);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 & 0x40404040u) {
+      const float4 u4 = *reinterpret_cast<const float4*>(u + idx);
+      const float4 v4 = *reinterpret_cast<const float4*>(v + idx);
+      const float4 w4 = *reinterpret_cast<const float4*>(w + idx);
+      const float4 vm = *reinterpret_cast<const float4*>(v + idx - g.nx);
+      const float4 wm = *reinterpret_cast<const float4*>(w + idx - g.plane);
+      const float ul = (c4 & B_XM) ? u[idx - 1] : 0.f;
+      const unsigned c0 = c4 & 0xffu, c1 = (c4 >> 8) & 0xffu, c2 = (c4 >> 16) & 0xffu, c3 = c4 >> 24;
+      if (c0 & B_FLUID) o.x = scale * quad_div(c0, u4.x, ul, v4.x, vm.x, w4.x, wm.x);
+      if (c1 & B_FLUID) o.y = scale * quad_div(c1, u4.y, u4.x, v4.y, vm.y, w4.y, wm.y);
+      if (c2 & B_FLUID) o.z = scale * quad_div(c2, u4.z, u4.y, v4.z, vm.z, w4.z, wm.z);
+      if (c3 & B_FLUID) o.w = scale * quad_div(c3, u4.w, u4.z, v4.w, vm.w, w4.w, wm.w);
+    }
+    *reinterpret_cast<float4*>(out + idx) = o;
+  }
+}
+
+// one face: returns the new velocity of the face between a cell (m0, p0) and its
+// + neighbour (m1, p1); see k_grad_sub
+__device__ __forceinline__ float grad_face(uint8_t m0, uint8_t m1, double p0, double p1, float f,
+                                           double kappa) {
+  const bool ns0 = is_nonsolid(m0), fl0 = (m0 == FLUID);
+  const bool ns1 = is_nonsolid(m1), fl1 = (m1 == FLUID);
+  if (ns0 && ns1 && (fl0 || fl1))
+    return (float)((double)f - kappa * ((fl1 ? p1 : 0.0) - (fl0 ? p0 : 0.0)));
+  if ((fl0 && !ns1) || (!ns0 && fl1)) return 0.f;
+  return f;
+}
+
+__global__ void __launch_bounds__(256)
+k_grad_sub4(Geo g, const uint8_t* __restrict__ media, const double* __restrict__ p,
+            float* __restrict__ u, float* __restrict__ v, float* __restrict__ w, double kappa) {
+  const long long nq = g.ncell >> 2;
+  const int qx = g.nx >> 2;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq;
+       q += (long long)gridDim.x * blockDim.x) {
+    const long long idx = q << 2;
+    const int i = (int)(q % qx) << 2;
+    const long long t = q / qx;
+    const int j = (int)(t % g.ny);
+    const unsigned m4 = *reinterpret_cast<const unsigned*>(media + idx);
+    const bool last_x = (i + 4 >= g.nx), last_y = (j == g.ny - 1);
+    // labels of the + neighbours (ABSENT outside the box; the z-halo holds the
+    // neighbouring slab's labels or ABSENT at the global end)
+    const unsigned mxr = last_x ? (unsigned)ABSENT : (unsigned)media[idx + 4];
+    const unsigned my4 = last_y ? 0xffffffffu : *reinterpret_cast<const unsigned*>(media + idx + g.nx);
+    const unsigned mz4 = *reinterpret_cast<const unsigned*>(media + idx + g.plane);
+    // any Fluid cell among the quad and its + neighbours?  otherwise nothing changes
+    auto has_fluid = [](unsigned x) {
+      const unsigned y = x ^ 0x01010101u;          // a byte is 0 where the label is FLUID (1)
+      return ((y - 0x01010101u) & ~y & 0x80808080u) != 0u;
+    };
+    if (!(has_fluid(m4) || has_fluid(my4) || has_fluid(mz4) || mxr == (unsigned)FLUID)) continue;
+    const uint8_t m[5] = {(uint8_t)(m4 & 0xffu), (uint8_t)((m4 >> 8) & 0xffu),
+                          (uint8_t)((m4 >> 16) & 0xffu), (uint8_t)(m4 >> 24), (uint8_t)mxr};
+    const double2 pa = *reinterpret_cast<const double2*>(p + idx);
+    const double2 pb = *reinterpret_cast<const double2*>(p + idx + 2);
+    const double px[5] = {pa.x, pa.y, pb.x, pb.y, (mxr == (unsigned)FLUID) ? p[idx + 4] : 0.0};
+    double py[4] = {0.0, 0.0, 0.0, 0.0}, pz[4];
+    if (!last_y) {
+      const double2 a = *reinterpret_cast<const double2*>(p + idx + g.nx);
+      const double2 b = *reinterpret_cast<const double2*>(p + idx + g.nx + 2);
+      py[0] = a.x; py[1] = a.y; py[2] = b.x; py[3] = b.y;
+    }
+    {
+      const double2 a = *reinterpret_cast<const double2*>(p + idx + g.plane);
+      const double2 b = *reinterpret_cast<const double2*>(p + idx + g.plane + 2);
+      pz[0] = a.x; pz[1] = a.y; pz[2] = b.x; pz[3] = b.y;
+    }
+    float4 u4 = *reinterpret_cast<const float4*>(u + idx);
+    float4 v4 = *reinterpret_cast<const float4*>(v + idx);
+    float4 w4 = *reinterpret_cast<const float4*>(w + idx);
+    float* uu = reinterpret_cast<float*>(&u4);
+    float* vv = reinterpret_cast<float*>(&v4);
+    float* ww = reinterpret_cast<float*>(&w4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uu[e] = grad_face(m[e], m[e + 1], px[e], px[e + 1], uu[e], kappa);
+      vv[e] = grad_face(m[e], (uint8_t)((my4 >> (8 * e)) & 0xffu), px[e], py[e], vv[e], kappa);
+      ww[e] = grad_face(m[e], (uint8_t)((mz4 >> (8 * e)) & 0xffu), px[e], pz[e], ww[e], kappa);
+    }
+    *reinterpret_cast<float4*>(u + idx) = u4;
+    *reinterpret_cast<float4*>(v + idx) = v4;
+    *reinterpret_cast<float4*>(w + idx) = w4;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_check4(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ u,
+         const float* __restrict__ v, const float* __restrict__ w, const double* __restrict__ p,
+         Scal* __restrict__ sc, double* __restrict__ partials) {
+  __shared__ double red[32];
+  float mx = 0.f;
+  unsigned bad = 0;
+  const long long nq = g.ncell >> 2;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq;
+       q += (long long)gridDim.x * blockDim.x) {
+    const long long idx = q << 2;
+    const unsigned c4 = *reinterpret_cast<const unsigned*>(codes + idx);
+    const float4 u4 = *reinterpret_cast<const float4*>(u + idx);
+    const float4 v4 = *reinterpret_cast<const float4*>(v + idx);
+    const float4 w4 = *reinterpret_cast<const float4*>(w + idx);
+    bad += !isfinite(u4.x) + !isfinite(u4.y) + !isfinite(u4.z) + !isfinite(u4.w);
+    bad += !isfinite(v4.x) + !isfinite(v4.y) + !isfinite(v4.z) + !isfinite(v4.w);
+    bad += !isfinite(w4.x) + !isfinite(w4.y) + !isfinite(w4.z) + !isfinite(w4.w);
+    if (c4 & 0x40404040u) {
+      const float4 vm = *reinterpret_cast<const float4*>(v + idx - g.nx);
+      const float4 wm = *reinterpret_cast<const float4*>(w + idx - g.plane);
+      const float ul = (c4 & B_XM) ? u[idx - 1] : 0.f;
+      const double2 pa = *reinterpret_cast<const double2*>(p + idx);
+      const double2 pb = *reinterpret_cast<const double2*>(p + idx + 2);
+      const unsigned c0 = c4 & 0xffu, c1 = (c4 >> 8) & 0xffu, c2 = (c4 >> 16) & 0xffu, c3 = c4 >> 24;
+      float d;
+      if (c0 & B_FLUID) {
+        bad += !isfinite(pa.x);
+        d = fabsf(quad_div(c0, u4.x, ul, v4.x, vm.x, w4.x, wm.x));
+        if (d == d) mx = fmaxf(mx, d);
+      }
+      if (c1 & B_FLUID) {
+        bad += !isfinite(pa.y);
+        d = fabsf(quad_div(c1, u4.y, u4.x, v4.y, vm.y, w4.y, wm.y));
+        if (d == d) mx = fmaxf(mx, d);
+      }
+      if (c2 & B_FLUID) {
+        bad += !isfinite(pb.x);
+        d = fabsf(quad_div(c2, u4.z, u4.y, v4.z, vm.z, w4.z, wm.z));
+        if (d == d) mx = fmaxf(mx, d);
+      }
+      if (c3 & B_FLUID) {
+        bad += !isfinite(pb.y);
+        d = fabsf(quad_div(c3, u4.w, u4.z, v4.w, vm.w, w4.w, wm.w));
+        if (d == d) mx = fmaxf(mx, d);
+      }
+    }
+  }
+  const double bm = block_max((double)mx, red);
+  const double bb = block_sum((double)bad, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = bm;
+    if (bb > 0.0) atomicAdd(&sc->nonfinite, (unsigned long long)bb);
+  }
+  if (last_block(&sc->ticketC, gridDim.x)) {
+    double m = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+      m = fmax(m, __ldcg(partials + b));
+    m = block_max(m, red);
+    if (threadIdx.x == 0) sc->gD[sc->rank] = m;
+  }
+}
+
 // ---- forces ---------------------------------------------------------------------
 // Forces.fs:6-12: v += gravity * dt on every Fluid cell.
 template <typename T>
