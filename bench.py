@@ -333,19 +333,26 @@ def run_cuda(args):
 
     # ---- the same step with the multigrid preconditioner, to tolerance (1 GPU) ---------------
     tol_mg = None
-    if not args.no_tolerance_run and world == 1 and args.precond != "mg":
+    if not args.no_tolerance_run and args.precond != "mg":
         s.close()
         s = None
+        nid2 = None
+        if world > 1:
+            box = [nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            nid2 = box[0]
         smg = Solver(n, n, n, dtype=np.float32, h=h_, rho=rho_, precond="mg", tol=1e-6,
-                     max_iters=2000, device=local)
+                     max_iters=2000, device=local, rank=rank, world=world, nz_global=nzg,
+                     z0=rank * n, nccl_id=nid2)
         smg.upload_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
         smg.snapshot()
         best = None
         for _ in range(3):
             smg.restore()
+            barrier()
             smg.timer_start()
             ti = smg.step(dt)
-            ms = smg.timer_stop()
+            ms = max_over_ranks(smg.timer_stop())
             if best is None or ms < best[0]:
                 best = (ms, ti)
         ms, ti = best

@@ -39,7 +39,7 @@ extern "C" {
 /* ---- enums ------------------------------------------------------------ */
 enum { SPL_F32 = 0, SPL_F64 = 1 };                          /* spl_desc.dtype  */
 enum { SPL_PC_NONE = 0, SPL_PC_JACOBI = 1, SPL_PC_RBIC0 = 2,
-       SPL_PC_MG = 3 /* geometric multigrid V-cycle, opt-in, world = 1 only */ }; /* .precond */
+       SPL_PC_MG = 3 /* geometric multigrid V-cycle (opt-in) */ }; /* .precond */
 enum { SPL_AIR = 0, SPL_FLUID = 1, SPL_SOLID = 2, SPL_ABSENT = 255 };
 
 /* quirk mask: reproduce the reference's literal Convection.fs behaviour

@@ -145,6 +145,12 @@ struct spl_ctx {
   int mg_coarse = 30;          // sweeps on the coarsest level, even (SPL_MG_COARSE)
   std::vector<double> mg_omega;  // per-sweep Jacobi weights: Chebyshev on [1/3, 2] (SPL_MG_OMEGA=w: constant)
   bool mg_sumform = false;     // SPL_MG_SUMFORM=1: N s - sum Laplacian in the marching kernels
+  // world > 1: the coarsest level is gathered and solved as ONE global grid on every rank
+  bool mg_gbottom = false;
+  Geo mg_gg{};                 // global geometry of the coarsest level
+  uint8_t* mg_gcodes = nullptr;
+  char *mg_gb = nullptr, *mg_gu = nullptr;
+  int mg_gsweeps = 100;        // Jacobi sweeps of the global coarsest solve (SPL_MG_GSWEEPS)
   bool mg_no_bottom = false;   // SPL_MG_NO_BOTTOM=1: per-level launches down to the coarsest level
   size_t mg_bottom_smem = 0;
   bool mg_no_march = false;    // SPL_MG_NO_MARCH=1: one-thread-per-cell kernels on every level
@@ -234,6 +240,25 @@ int exchange_halo(spl_ctx* c, char* plane0, size_t es, ncclDataType_t ty, int wi
   if (c->d.rank < c->d.world - 1) {
     NC(g_nccl.Send(plane0 + (size_t)(g.nz - width) * pb, cnt, ty, c->d.rank + 1, c->comm,
                    c->stream));
+    NC(g_nccl.Recv(plane0 + (size_t)g.nz * pb, cnt, ty, c->d.rank + 1, c->comm, c->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  return SPL_OK;
+}
+
+// one z-plane of a field of any multigrid level (plane0 = its plane 0, halo >= 1)
+int exchange_level(spl_ctx* c, const Geo& g, void* plane0_, size_t es, ncclDataType_t ty) {
+  if (c->d.world <= 1) return SPL_OK;
+  char* plane0 = static_cast<char*>(plane0_);
+  const size_t cnt = (size_t)g.plane;
+  const size_t pb = cnt * es;
+  NC(g_nccl.GroupStart());
+  if (c->d.rank > 0) {
+    NC(g_nccl.Send(plane0, cnt, ty, c->d.rank - 1, c->comm, c->stream));
+    NC(g_nccl.Recv(plane0 - pb, cnt, ty, c->d.rank - 1, c->comm, c->stream));
+  }
+  if (c->d.rank < c->d.world - 1) {
+    NC(g_nccl.Send(plane0 + (size_t)(g.nz - 1) * pb, cnt, ty, c->d.rank + 1, c->comm, c->stream));
     NC(g_nccl.Recv(plane0 + (size_t)g.nz * pb, cnt, ty, c->d.rank + 1, c->comm, c->stream));
   }
   NC(g_nccl.GroupEnd());
@@ -489,15 +514,23 @@ struct Impl {
     }
   }
 
-  static void vcycle(spl_ctx* c, int par) {
+  static int vcycle(spl_ctx* c, int par) {
     const int L = (int)c->mg.size();
     const int nu = c->mg_nu;
     const std::vector<double>& om = c->mg_omega;   // per-sweep weights (size nu)
     std::vector<char*> cur(L, nullptr), nxt(L, nullptr);
     auto other = [&](int l, char* b) { return b == c->mg[l].u ? c->mg[l].tmp : c->mg[l].u; };
+    // z-slabs: the neighbouring slab's boundary plane of every field a later pass reads
+    // through the z stencil travels into the halo right after the pass that wrote it
+    int xrc = SPL_OK;
+    auto xch = [&](int l, char* buf) {
+      if (c->d.world > 1 && xrc == SPL_OK)
+        xrc = exchange_level(c, c->mg[l].g, buf, sizeof(T), nccl_real(c));
+    };
     auto advance_buf = [&](int l) {
       cur[l] = nxt[l];
       nxt[l] = other(l, cur[l]);
+      xch(l, cur[l]);
     };
     auto simple_smooth = [&](int l, int first, double omega) {
       MgLevel& v = c->mg[l];
@@ -537,11 +570,13 @@ struct Impl {
       if (mg_fast(c, v) && ((l == L - 1) ? k >= 2 : nu >= 2)) k -= 1;   // FIRST2 = 2 sweeps
       nxt[l] = (k & 1) ? v.u : v.tmp;
     }
+    xch(0, c->mg[0].b);   // r
     // levels [lb, L) fit one CTA's shared memory: a single launch runs their sub-cycle
     int lb = L;
     if (L >= 2 && !c->mg_no_bottom)
       for (int l = 0; l < L; ++l)
         if (c->mg[l].g.ncell <= MG_BOTTOM_CELLS && L - l <= MG_BOTTOM_LEVELS) { lb = l; break; }
+    if (c->mg_gbottom) lb = L;               // z-slabs: global coarsest solve instead
     const int ldown = lb < L ? lb : L - 1;   // levels [0, ldown) smooth + restrict
     for (int l = 0; l < ldown; ++l) {
       MgLevel& f = c->mg[l];
@@ -553,8 +588,45 @@ struct Impl {
         LAUNCH(c, k_mg_restrict<T>, grid_for(c, k.g.ncell), 256, f.g, f.codes, P(cur[l]),
                P(f.b), T(f.scale), k.g, k.codes, P(k.b), c->sc);
       }
+      xch(l + 1, k.b);
     }
-    if (lb < L) {
+    if (c->mg_gbottom) {
+      // every rank gathers the coarsest right-hand side (z-slabs concatenate into the
+      // global array), solves the global coarsest grid in one CTA, and takes its own
+      // planes plus the two halo planes out of the global solution
+      MgLevel& k = c->mg[L - 1];
+      const Geo& gg = c->mg_gg;
+      if (xrc == SPL_OK) {
+        ncclResult_t r_ = g_nccl.AllGather(k.b, c->mg_gb, (size_t)k.g.ncell, nccl_real(c),
+                                           c->comm, c->stream);
+        if (r_ != ncclSuccess) xrc = fail(c, SPL_E_CUDA, "NCCL error %d in the multigrid gather", (int)r_);
+      }
+      MgBottomArgs<T> a{};
+      a.nlev = 1;
+      a.nu = nu;
+      a.coarse_sweeps = c->mg_gsweeps;
+      a.g[0] = gg;
+      a.codes[0] = c->mg_gcodes;
+      a.scale[0] = T(k.scale);
+      for (int i = 0; i < nu; ++i) a.omega[i] = T(om[i]);
+      a.b0 = P(c->mg_gb);
+      a.u0 = P(c->mg_gu);
+      a.sc = c->sc;
+      const size_t smem = mg_bottom_smem<T>(a.g, 1);
+      if (smem > c->mg_bottom_smem) {
+        cudaFuncSetAttribute(k_mg_bottom<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        c->mg_bottom_smem = smem;
+      }
+      k_mg_bottom<T><<<1, 1024, smem, c->stream>>>(a);
+      c->launches++;
+      const int zlo = k.g.z0 > 0 ? k.g.z0 - 1 : 0;
+      const int zhi = (k.g.z0 + k.g.nz < gg.nz) ? k.g.z0 + k.g.nz + 1 : gg.nz;
+      const size_t pb = (size_t)gg.plane * sizeof(T);
+      cudaMemcpyAsync(k.u + ((long long)zlo - k.g.z0) * (long long)pb, c->mg_gu + (size_t)zlo * pb,
+                      (size_t)(zhi - zlo) * pb, cudaMemcpyDeviceToDevice, c->stream);
+      cur[L - 1] = k.u;
+    } else if (lb < L) {
       MgBottomArgs<T> a{};
       a.nlev = L - lb;
       a.nu = nu;
@@ -577,6 +649,7 @@ struct Impl {
       k_mg_bottom<T><<<1, 1024, smem, c->stream>>>(a);
       c->launches++;
       cur[lb] = c->mg[lb].u;
+      xch(lb, cur[lb]);
     } else {
       smooth_from_zero(L - 1, (L == 1) ? 2 * nu : c->mg_coarse, L == 1);
     }
@@ -600,22 +673,25 @@ struct Impl {
       } else {
         LAUNCH(c, k_mg_prolong<T>, grid_for(c, f.g.ncell), 256, f.g, f.codes, P(cur[l]), k.g,
                P(cur[l + 1]), c->sc);
+        xch(l, cur[l]);
         for (int s = 0; s < nu; ++s) simple_smooth(l, 0, om[nu - 1 - s]);
       }
     }
     if (!dot_done)
       LAUNCH(c, k_dot_rz<T>, grid_for(c, c->g.ncell), 256, c->g, P(c->r), P(c->z), c->sc,
              c->partials, par);
+    return xrc;
   }
 
-  static void precondition(spl_ctx* c, int par) {
-    if (c->d.precond == SPL_PC_MG) { vcycle(c, par); return; }
+  static int precondition(spl_ctx* c, int par) {
+    if (c->d.precond == SPL_PC_MG) return vcycle(c, par);
     const Geo& g = c->g;
     const int grid = grid_for(c, g.ncell);
     LAUNCH(c, (k_rb_sweep<T, 1>), grid, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc,
            c->partials, par);
     LAUNCH(c, (k_rb_sweep<T, 0>), grid, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc,
            c->partials, par);
+    return SPL_OK;
   }
 
   static int build_rbic0(spl_ctx* c) {
@@ -664,9 +740,9 @@ struct Impl {
     // rho_0 = r.z, max|b|  (phase B with alpha = 0)
     LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
            c->sc, c->partials, 0, 1, m);
-    if (pc_explicit_z(PC)) precondition(c, 0);
-    int rc = gather_slots(c, &c->sc->gBM[0][0][0], 2);
-    if (rc) return rc;
+    int rc = SPL_OK;
+    if (pc_explicit_z(PC) && (rc = precondition(c, 0))) return rc;
+    if ((rc = gather_slots(c, &c->sc->gBM[0][0][0], 2))) return rc;
     LAUNCH(c, k_set_bmax, 1, 1, c->sc);
     CU(cudaGetLastError());
 
@@ -700,7 +776,7 @@ struct Impl {
         LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
                c->sc, c->partials, par, 0, m);
         if (prof) CU(cudaEventRecord(c->pev[3 * c->profile_iters + (it - 1)], c->stream));
-        if (pc_explicit_z(PC)) precondition(c, par);   // z = M^-1 r, rho = r.z
+        if (pc_explicit_z(PC) && (rc = precondition(c, par))) return rc;   // z = M^-1 r, rho = r.z
         if ((rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
         if (it % m == 0) {   // every buffer holds an unflushed direction: x += sum alpha s
           const bool pf = c->profile_iters > 0 && nflush < 64;
@@ -895,6 +971,9 @@ void spl_destroy(spl_ctx* c) {
   for (MgLevel& l : c->mg)
     for (void* p : l.allocs)
       if (p) cudaFree(p);
+  if (c->mg_gcodes) cudaFree(c->mg_gcodes);
+  if (c->mg_gb) cudaFree(c->mg_gb);
+  if (c->mg_gu) cudaFree(c->mg_gu);
   if (c->mloc) cudaFree(c->mloc);
   if (c->mold) cudaFree(c->mold);
   if (c->mnew) cudaFree(c->mnew);
@@ -991,8 +1070,6 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if ((rc = alloc_field(c, 24, 1, &tmp, 0xFF))) return rc;   // BFS layers (spl_cleanup)
   c->layer = reinterpret_cast<uint8_t*>(tmp);
   if (d.precond == SPL_PC_MG) {
-    if (d.world > 1)
-      return fail(c, SPL_E_BADARG, "SPL_PC_MG supports one GPU per box (world = 1) only");
     if (const char* e = getenv("SPL_MG_NU")) c->mg_nu = atoi(e) > 0 ? atoi(e) : 2;
     if (const char* e = getenv("SPL_MG_NO_MARCH")) c->mg_no_march = atoi(e) != 0;
     if (const char* e = getenv("SPL_MG_SUMFORM")) c->mg_sumform = atoi(e) != 0;
@@ -1021,9 +1098,13 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
       if (f.ny > 1 && f.ny < mind) mind = f.ny;
       if (f.nz > 1 && f.nz < mind) mind = f.nz;
       if (mind <= 8 || mind == (1 << 30)) break;
+      // z-slabs coarsen in lock step: every rank must hold whole coarse planes
+      if (d.world > 1 && ((f.nz & 1) || (f.z0 & 1) || (f.nzg & 1))) break;
       MgLevel l;
       l.g.nx = (f.nx + 1) / 2; l.g.ny = (f.ny + 1) / 2; l.g.nz = (f.nz + 1) / 2;
-      l.g.hz = 1; l.g.z0 = 0; l.g.nzg = l.g.nz;
+      l.g.hz = 1;
+      l.g.z0 = (d.world > 1) ? f.z0 / 2 : 0;
+      l.g.nzg = (d.world > 1) ? f.nzg / 2 : l.g.nz;
       l.g.plane = (long long)l.g.nx * l.g.ny;
       l.g.ncell = l.g.plane * l.g.nz;
       l.scale = c->mg.back().scale * 0.25;
@@ -1039,6 +1120,24 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
       l.codes = reinterpret_cast<uint8_t*>(base[1]);
       l.u = base[2]; l.b = base[3]; l.tmp = base[4];
       c->mg.push_back(l);
+    }
+    // z-slabs: gather the coarsest level into one global grid when the slabs are equal
+    // and the global grid fits one CTA's shared memory (otherwise the bottom of the cycle
+    // stays local to each slab: a weaker, still symmetric, preconditioner)
+    if (d.world > 1 && c->mg.size() >= 2 && !getenv("SPL_MG_LOCAL_BOTTOM")) {
+      const Geo& k = c->mg.back().g;
+      Geo gg = k;
+      gg.nz = k.nzg; gg.z0 = 0; gg.ncell = gg.plane * gg.nz;
+      const bool equal = (long long)k.nz * d.world == k.nzg && k.z0 == d.rank * k.nz;
+      const size_t smem = (size_t)gg.ncell * (3 * c->esz + 1) + 64;
+      if (equal && smem <= 200 * 1024) {
+        c->mg_gbottom = true;
+        c->mg_gg = gg;
+        CU(cudaMalloc(&c->mg_gcodes, (size_t)gg.ncell));
+        CU(cudaMalloc(&c->mg_gb, (size_t)gg.ncell * c->esz));
+        CU(cudaMalloc(&c->mg_gu, (size_t)gg.ncell * c->esz));
+        if (const char* e = getenv("SPL_MG_GSWEEPS")) c->mg_gsweeps = atoi(e) > 1 ? atoi(e) : 100;
+      }
     }
   }
   CU(cudaMalloc(&c->sc, sizeof(Scal)));
@@ -1090,12 +1189,21 @@ static int rebuild_operators(spl_ctx* c) {
     rc = DISPATCH(c, Impl<float>::build_rbic0(c), Impl<double>::build_rbic0(c));
     if (rc) return rc;
   }
-  for (size_t l = 1; l < c->mg.size(); ++l) {   // SPL_PC_MG: coarse labels and stencil codes
+  // SPL_PC_MG: coarse labels and stencil codes.  With z-slabs the smoothers read the
+  // labels / codes of the neighbouring slab's boundary plane through the halo.
+  if (!c->mg.empty() && (rc = exchange_level(c, g, c->codes, 1, ncclUint8))) return rc;
+  for (size_t l = 1; l < c->mg.size(); ++l) {
     MgLevel& f = c->mg[l - 1];
     MgLevel& k = c->mg[l];
     LAUNCH(c, k_mg_coarsen, grid_for(c, k.g.ncell), 256, f.g, f.media, k.g, k.media);
+    if ((rc = exchange_level(c, k.g, k.media, 1, ncclUint8))) return rc;
     LAUNCH(c, k_codes, grid_for(c, k.g.ncell), 256, k.g, k.media, k.codes);
     CU(cudaGetLastError());
+    if ((rc = exchange_level(c, k.g, k.codes, 1, ncclUint8))) return rc;
+  }
+  if (c->mg_gbottom) {
+    MgLevel& k = c->mg.back();
+    NC(g_nccl.AllGather(k.codes, c->mg_gcodes, (size_t)k.g.ncell, ncclUint8, c->comm, c->stream));
   }
   return SPL_OK;
 }
@@ -1585,8 +1693,9 @@ int spl_apply_preconditioner(spl_ctx* c, const void* r, void* z, float* ms) {
   h->world = 1;
   CU(cudaMemcpyAsync(c->sc, h, sizeof(Scal), cudaMemcpyHostToDevice, c->stream));
   CU(cudaEventRecord(c->tev[0], c->stream));
-  if (c->d.dtype == SPL_F64) Impl<double>::precondition(c, 0);
-  else Impl<float>::precondition(c, 0);
+  int prc = (c->d.dtype == SPL_F64) ? Impl<double>::precondition(c, 0)
+                                    : Impl<float>::precondition(c, 0);
+  if (prc) return prc;
   CU(cudaEventRecord(c->tev[1], c->stream));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(z, c->z, bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -196,8 +196,18 @@ k_mg_bottom(const MgBottomArgs<T> a) {
     }
   }
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int l = 0; l < a.nlev; ++l)
-    for (int i = tid; i < (int)a.g[l].ncell; i += nt) C[l][i] = a.codes[l][i];
+  // the sub-cycle is local to this z-slab: faces towards a neighbouring slab are closed
+  // (the z bits of the first / last local plane are cleared; they are 0 at the global
+  // ends anyway), so with world > 1 the bottom of the cycle is block-diagonal
+  for (int l = 0; l < a.nlev; ++l) {
+    const int pl = (int)a.g[l].plane, nc = (int)a.g[l].ncell;
+    for (int i = tid; i < nc; i += nt) {
+      unsigned cd = a.codes[l][i];
+      if (i < pl) cd &= ~(unsigned)B_ZM;
+      if (i >= nc - pl) cd &= ~(unsigned)B_ZP;
+      C[l][i] = (uint8_t)cd;
+    }
+  }
   for (int i = tid; i < (int)a.g[0].ncell; i += nt) B[0][i] = a.b0[i];
   __syncthreads();
 

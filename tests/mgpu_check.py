@@ -26,7 +26,8 @@ from splashy_b200 import Solver, nccl_unique_id, scenes  # noqa: E402
 from splashy_b200.slab import SlabPlan  # noqa: E402
 
 
-def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=False):
+def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=False,
+             precond="jacobi"):
     plan = SlabPlan(nzg, world, uneven=uneven)
     z0, nz = plan.z0(rank), plan.nz(rank)
     whole = scenes.vortex(nx, ny, nzg, cfl=2.0, dtype=dtype)
@@ -34,7 +35,7 @@ def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=
     dt = whole["dt"]
     tol = 1e-6 if dtype == np.float32 else 1e-10
     with Solver(nx, ny, nz, dtype=dtype, tol=tol, device=local, rank=rank, world=world,
-                nz_global=nzg, z0=z0, nccl_id=nid) as s:
+                nz_global=nzg, z0=z0, nccl_id=nid, precond=precond) as s:
         s.upload(part["labels"], part["U"], part["V"], part["W"])
         if fixed:
             s.set_fixed_iters(fixed)
@@ -55,7 +56,7 @@ def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=
             dist.send(t, dst=0)
     res = None
     if rank == 0:
-        with Solver(nx, ny, nzg, dtype=dtype, tol=tol, device=local) as s1:
+        with Solver(nx, ny, nzg, dtype=dtype, tol=tol, device=local, precond=precond) as s1:
             s1.upload(whole["labels"], whole["U"], whole["V"], whole["W"])
             if fixed:
                 s1.set_fixed_iters(fixed)
@@ -76,7 +77,14 @@ def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=
               and info["max_abs_div"] <= (1e-4 if dtype == np.float32 else 1e-8) * vs)
         if fixed:
             ok = err_one <= lim and info["iters"] == fixed
-        res = {"case": name, "ok": bool(ok), "world": world, "iters_slab": info["iters"],
+        if precond == "mg":
+            # the slab hierarchy (levels stop where a rank runs out of planes, the bottom
+            # of the cycle is block-local) is a different -- equally valid -- preconditioner
+            # than the one-GPU hierarchy: same converged answer, iteration counts reported
+            ok = (err_orc <= lim and err_one <= lim and info["converged"] == 1
+                  and info["iters"] <= 3 * info1["iters"] + 5
+                  and info["max_abs_div"] <= (1e-4 if dtype == np.float32 else 1e-8) * vs)
+        res = {"case": name, "precond": precond, "ok": bool(ok), "world": world, "iters_slab": info["iters"],
                "iters_one_gpu": info1["iters"], "iters_oracle": oinfo["iters"],
                "vel_err_vs_one_gpu": err_one, "vel_err_vs_oracle": err_orc,
                "p_err_vs_one_gpu": perr, "max_abs_div": info["max_abs_div"],
@@ -95,10 +103,18 @@ def main():
              ("vortex_f64", 36, 20, 12 * world, np.float64, 0, False),
              ("vortex_f32_fixed", 64, 48, 16 * world, np.float32, 25, False),
              ("vortex_f64_uneven", 23, 17, 9 * world + 3, np.float64, 0, True)]
-    for name, nx, ny, nzg, dtype, fixed, uneven in cases:
+    cases = [c + ("jacobi",) for c in cases]
+    cases += [("mg_f32_march_bottom", 128, 64, 32 * world, np.float32, 0, False, "mg"),
+              ("mg_f32_small", 64, 48, 16 * world, np.float32, 0, False, "mg"),
+              ("mg_f64", 36, 20, 12 * world, np.float64, 0, False, "mg")]
+    only = os.environ.get("MGPU_ONLY")
+    for name, nx, ny, nzg, dtype, fixed, uneven, precond in cases:
+        if only and only not in name:
+            continue
         box = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        r = run_case(name, nx, ny, nzg, dtype, world, rank, local, box[0], fixed, uneven)
+        r = run_case(name, nx, ny, nzg, dtype, world, rank, local, box[0], fixed, uneven,
+                     precond)
         if rank == 0:
             results.append(r)
         dist.barrier()
