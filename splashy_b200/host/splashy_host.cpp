@@ -287,6 +287,130 @@ void Solver::check(const Grid& g, const std::vector<Coord>& markers) {
   fail_if(spl_check(ctx_, 0.0001, &info));   // Pressure.fs:148 threshold
 }
 
+// ---- Simulator ----------------------------------------------------------------------
+Simulator::Simulator(unsigned quirks, double tol, int margin, int device)
+    : quirks_(quirks), tol_(tol), margin_(margin), device_(device) {}
+
+Simulator::~Simulator() {
+  if (ctx_) spl_destroy(ctx_);
+}
+
+void Simulator::fail_if(int rc) {
+  if (rc != SPL_OK) throw Failure(spl_last_error(ctx_));
+}
+
+void Simulator::generate(const std::vector<Coord>& marker_cells) {
+  std::vector<Coord> ms;
+  for (const Coord& c : marker_cells) ms.push_back(Coord::construct(c.x, c.y, c.z));
+  // Set.ofList: sorted by Coord.compare (x, then y, then z), duplicates dropped
+  std::sort(ms.begin(), ms.end(), [](const Coord& a, const Coord& b) {
+    return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z);
+  });
+  ms.erase(std::unique(ms.begin(), ms.end()), ms.end());
+  locations_.clear();
+  for (const Coord& m : ms) locations_.emplace_back((double)m.x, (double)m.y, (double)m.z);
+  // Build.setup (fun () -> Build.add_new_markers markers |> Grid.add_cells)
+  const float wh = 100.0f + (float)Constants::h_int / 2.0f;            // Constants.fs:32
+  std::vector<std::pair<Coord, Cell>> fresh;
+  for (const Coord& m : ms) {
+    const bool in_world = std::fabs((float)m.x) <= wh && std::fabs((float)m.y) <= wh &&
+                          std::fabs((float)m.z) <= wh;                  // World.contains
+    if (!grid_.get(m) && in_world) {
+      Cell c;
+      c.media = Media::Fluid;
+      fresh.insert(fresh.begin(), {m, c});
+    }
+  }
+  grid_.add_cells(fresh);
+  uploaded_ = false;
+}
+
+void Simulator::set_velocity(const Coord& where, const Vector3d& v) {
+  if (uploaded_) throw Failure("set_velocity after the first advance");
+  grid_.update_velocities({{where, v}});
+}
+
+void Simulator::ensure_uploaded() {
+  if (uploaded_) return;
+  Box b = pack(grid_);
+  // room for Build.max_distance rings plus the cells a marker can reach
+  Box big;
+  big.ox = b.ox - margin_; big.oy = b.oy - margin_; big.oz = b.oz - margin_;
+  big.nx = b.nx + 2 * margin_; big.ny = b.ny + 2 * margin_; big.nz = b.nz + 2 * margin_;
+  const size_t n = (size_t)big.nx * big.ny * big.nz;
+  big.media.assign(n, SPL_ABSENT);
+  big.u.assign(n, 0.0); big.v.assign(n, 0.0); big.w.assign(n, 0.0); big.p.assign(n, 0.0);
+  for (int k = 0; k < b.nz; ++k)
+    for (int j = 0; j < b.ny; ++j)
+      for (int i = 0; i < b.nx; ++i) {
+        const size_t s = ((size_t)k * b.ny + j) * b.nx + i;
+        const size_t d = ((size_t)(k + margin_) * big.ny + (j + margin_)) * big.nx + (i + margin_);
+        big.media[d] = b.media[s];
+        big.u[d] = b.u[s]; big.v[d] = b.v[s]; big.w[d] = b.w[s]; big.p[d] = b.p[s];
+      }
+  box_ = std::move(big);
+  if (ctx_) spl_destroy(ctx_);
+  ctx_ = nullptr;
+  spl_desc d;
+  spl_desc_default(&d);
+  d.nx = box_.nx; d.ny = box_.ny; d.nz = box_.nz;
+  d.dtype = SPL_F64;
+  d.tol = tol_;
+  d.quirks = quirks_;
+  d.origin[0] = box_.ox; d.origin[1] = box_.oy; d.origin[2] = box_.oz;
+  d.device = device_;
+  if (spl_create(&ctx_, &d) != SPL_OK) throw Failure(spl_last_error(nullptr));
+  fail_if(spl_upload(ctx_, box_.media.data(), box_.u.data(), box_.v.data(), box_.w.data(),
+                     box_.p.data()));
+  const int l = (int)((100.0f + (float)Constants::h_int / 2.0f) / (float)Constants::h_int);
+  const int lo[3] = {-l - box_.ox, -l - box_.oy, -l - box_.oz};
+  const int hi[3] = {l - box_.ox, l - box_.oy, l - box_.oz};
+  fail_if(spl_set_world(ctx_, lo, hi));
+  std::vector<double> xyz;
+  for (const Vector3d& v : locations_) { xyz.push_back(v.x); xyz.push_back(v.y); xyz.push_back(v.z); }
+  fail_if(spl_set_markers(ctx_, (int64_t)locations_.size(), xyz.data()));
+  uploaded_ = true;
+}
+
+void Simulator::advance(double dt, bool sanity) {
+  ensure_uploaded();
+  spl_info info;
+  fail_if(spl_advance(ctx_, dt, sanity ? 1 : 0, &info));
+  last_iters_ = info.iters;
+  std::vector<double> xyz(3 * locations_.size());
+  fail_if(spl_get_markers(ctx_, xyz.data()));
+  for (size_t m = 0; m < locations_.size(); ++m)
+    locations_[m] = Vector3d(xyz[3 * m], xyz[3 * m + 1], xyz[3 * m + 2]);
+}
+
+std::vector<Coord> Simulator::markers() const {
+  std::vector<Coord> out;
+  for (const Vector3d& l : locations_) out.push_back(Coord::construct(l.x, l.y, l.z));
+  return out;
+}
+
+Grid Simulator::snapshot() {
+  if (!uploaded_) return grid_;
+  fail_if(spl_download(ctx_, box_.u.data(), box_.v.data(), box_.w.data(), box_.p.data(), nullptr));
+  fail_if(spl_download_media(ctx_, box_.media.data()));
+  Grid g;
+  std::vector<std::pair<Coord, Cell>> cells;
+  const int h = Constants::h_int;
+  for (int k = 0; k < box_.nz; ++k)
+    for (int j = 0; j < box_.ny; ++j)
+      for (int i = 0; i < box_.nx; ++i) {
+        const size_t idx = ((size_t)k * box_.ny + j) * box_.nx + i;
+        if (box_.media[idx] == SPL_ABSENT) continue;
+        Cell c;
+        c.media = (Media)box_.media[idx];
+        c.velocity = Vector3d(box_.u[idx], box_.v[idx], box_.w[idx]);
+        if (c.media != Media::Solid) c.pressure = box_.p[idx];
+        cells.push_back({Coord{(i + box_.ox) * h, (j + box_.oy) * h, (k + box_.oz) * h}, c});
+      }
+  g.add_cells(cells);
+  return g;
+}
+
 }  // namespace splashy
 
 // ---------------------------------------------------------------------------------------
@@ -398,6 +522,50 @@ int splh_pressure(void* hp, const int* markers, int n, double dt, int* iters) {
 int splh_checks(void* hp, const int* markers, int n) {
   Host* h = static_cast<Host*>(hp);
   return guarded([&] { h->solver->check(h->grid, coords_of(markers, n)); });
+}
+
+// ---- Simulator (state on the device) ---------------------------------------------------
+void* splh_sim_new(unsigned quirks, double tol, int margin) {
+  return new Simulator(quirks, tol, margin);
+}
+void splh_sim_free(void* s) { delete static_cast<Simulator*>(s); }
+int splh_sim_generate(void* s, const int* cells, int n) {
+  return guarded([&] { static_cast<Simulator*>(s)->generate(coords_of(cells, n)); });
+}
+int splh_sim_set_velocity(void* s, int x, int y, int z, double vx, double vy, double vz) {
+  return guarded([&] {
+    static_cast<Simulator*>(s)->set_velocity({x, y, z}, Vector3d(vx, vy, vz));
+  });
+}
+int splh_sim_advance(void* s, double dt, int sanity) {
+  return guarded([&] { static_cast<Simulator*>(s)->advance(dt, sanity != 0); });
+}
+int splh_sim_marker_count(void* s) { return (int)static_cast<Simulator*>(s)->locations().size(); }
+int splh_sim_locations(void* s, double* xyz) {
+  return guarded([&] {
+    const auto& l = static_cast<Simulator*>(s)->locations();
+    for (size_t m = 0; m < l.size(); ++m) { xyz[3 * m] = l[m].x; xyz[3 * m + 1] = l[m].y; xyz[3 * m + 2] = l[m].z; }
+  });
+}
+// the grid as flat arrays: returns the cell count; call with null pointers to size them
+int splh_sim_snapshot(void* s, int cap, int* xyz, int* media, double* vel, double* p) {
+  int count = -1;
+  const int rc = guarded([&] {
+    Grid g = static_cast<Simulator*>(s)->snapshot();
+    count = (int)g.size();
+    if (!xyz) return;
+    int m = 0;
+    for (const auto& kv : g.cells()) {
+      if (m >= cap) break;
+      xyz[3 * m] = kv.first.x; xyz[3 * m + 1] = kv.first.y; xyz[3 * m + 2] = kv.first.z;
+      media[m] = (int)kv.second.media;
+      vel[3 * m] = kv.second.velocity.x; vel[3 * m + 1] = kv.second.velocity.y;
+      vel[3 * m + 2] = kv.second.velocity.z;
+      p[m] = kv.second.pressure.value_or(0.0);
+      ++m;
+    }
+  });
+  return rc ? -1 : count;
 }
 
 }  // extern "C"

@@ -144,4 +144,43 @@ class Solver {
   uint64_t projected_version_ = 0;
 };
 
+// Simulator.fs:19-129 with the state resident on the device: `generate` packs the
+// grid once (with a margin for the cells Build.setup creates), hands the marker
+// locations over, and every `advance` is one spl_advance call -- move_markers,
+// Build.setup block, convection, forces, viscosity, pressure (+ checks), cleanup.
+// The grid is unpacked only on request (`snapshot`).
+class Simulator {
+ public:
+  explicit Simulator(unsigned quirks = 0, double tol = 1e-12, int margin = 4, int device = 0);
+  ~Simulator();
+  Simulator(const Simulator&) = delete;
+  Simulator& operator=(const Simulator&) = delete;
+
+  // Simulator.generate (:113-129) for a given list of marker cells (the reference draws
+  // them from System.Random(12349)): markers = sorted distinct cells, locations = their
+  // centres, grid = the markers as new Fluid cells (Build.add_new_markers)
+  void generate(const std::vector<Coord>& marker_cells);
+  // overwrite a cell's velocity before the run (test scenes)
+  void set_velocity(const Coord& where, const Vector3d& v);
+  // Simulator.advance dt sanity (:54-110)
+  void advance(double dt, bool sanity);
+  const std::vector<Vector3d>& locations() const { return locations_; }   // metres
+  std::vector<Coord> markers() const;                                     // closest cells
+  Grid snapshot();                     // device state -> sparse grid (absent cells dropped)
+  int last_iterations() const { return last_iters_; }
+
+ private:
+  void fail_if(int rc);
+  void ensure_uploaded();
+  spl_ctx* ctx_ = nullptr;
+  Grid grid_;                          // host copy, valid until the first advance
+  Box box_;
+  std::vector<Vector3d> locations_;
+  unsigned quirks_;
+  double tol_;
+  int margin_, device_;
+  int last_iters_ = 0;
+  bool uploaded_ = false;
+};
+
 }  // namespace splashy

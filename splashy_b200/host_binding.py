@@ -40,6 +40,16 @@ def load():
         getattr(lib, name).argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_double]
     lib.splh_pressure.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_double, C.POINTER(C.c_int)]
     lib.splh_checks.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    lib.splh_sim_new.restype = C.c_void_p
+    lib.splh_sim_new.argtypes = [C.c_uint, C.c_double, C.c_int]
+    lib.splh_sim_free.argtypes = [C.c_void_p]
+    lib.splh_sim_generate.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    lib.splh_sim_set_velocity.argtypes = [C.c_void_p] + [C.c_int] * 3 + [C.c_double] * 3
+    lib.splh_sim_advance.argtypes = [C.c_void_p, C.c_double, C.c_int]
+    lib.splh_sim_marker_count.argtypes = [C.c_void_p]
+    lib.splh_sim_locations.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.splh_sim_snapshot.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -125,3 +135,55 @@ class Host:
     def checks(self, markers):
         a, n = self._markers(markers)
         self._ok(self._lib.splh_checks(self._h, a, n))
+
+
+class Simulator:
+    """The C++ mirror of Simulator.fs (generate / advance) with the state kept on the GPU."""
+
+    def __init__(self, quirks: int = 0, tol: float = 1e-12, margin: int = 4):
+        self._lib = load()
+        self._s = C.c_void_p(self._lib.splh_sim_new(quirks, tol, margin))
+
+    def close(self):
+        if self._s:
+            self._lib.splh_sim_free(self._s)
+            self._s = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ok(self, rc):
+        if rc != 0:
+            raise HostFailure(self._lib.splh_last_error().decode())
+
+    def generate(self, marker_cells):
+        a, n = Host._markers(marker_cells)
+        self._ok(self._lib.splh_sim_generate(self._s, a, n))
+
+    def set_velocity(self, coord, v):
+        self._ok(self._lib.splh_sim_set_velocity(self._s, *coord, *v))
+
+    def advance(self, dt: float, sanity: bool = True):
+        self._ok(self._lib.splh_sim_advance(self._s, dt, 1 if sanity else 0))
+
+    def locations(self):
+        n = self._lib.splh_sim_marker_count(self._s)
+        out = (C.c_double * (3 * n))()
+        self._ok(self._lib.splh_sim_locations(self._s, out))
+        return [tuple(out[3 * m:3 * m + 3]) for m in range(n)]
+
+    def snapshot(self):
+        """{(x, y, z): (media, (vx, vy, vz), pressure)} of every existing cell."""
+        n = self._lib.splh_sim_snapshot(self._s, 0, None, None, None, None)
+        if n < 0:
+            raise HostFailure(self._lib.splh_last_error().decode())
+        xyz, media = (C.c_int * (3 * n))(), (C.c_int * n)()
+        vel, p = (C.c_double * (3 * n))(), (C.c_double * n)()
+        got = self._lib.splh_sim_snapshot(self._s, n, xyz, media, vel, p)
+        if got < 0:
+            raise HostFailure(self._lib.splh_last_error().decode())
+        return {tuple(xyz[3 * m:3 * m + 3]): (media[m], tuple(vel[3 * m:3 * m + 3]), p[m])
+                for m in range(n)}

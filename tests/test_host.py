@@ -157,3 +157,37 @@ def test_adjacent_markers_pass_the_check_the_reference_fails():
             h.add_cell(c, cell.media, tuple(rng.uniform(-1, 1, 3)), cell.pressure)
         h.pressure(sim.markers, 0.016671)
         h.checks(sim.markers)
+
+
+@pytest.mark.gpu
+def test_simulator_mirror_runs_the_whole_advance_on_the_device():
+    """Simulator.generate + three Simulator.advance steps through the C++ mirror (state on
+    the GPU, every quirk flag) == the transcription (oracle/sparse_ref.py), cell by cell."""
+    dt = 0.016671
+    v0 = (0.3, -0.2, 0.5)
+    sim = sr.Simulator()
+    sim.generate(1, marker_cells=[(0, 0, 0)])
+    sim.grid.update_velocities([((0, 0, 0), v0)])
+    with hb.Simulator(quirks=63, tol=1e-14) as h:
+        h.generate([(0, 0, 0)])
+        h.set_velocity((0, 0, 0), v0)
+        for step in range(3):
+            sim.advance(dt, sanity=False)
+            h.advance(dt, sanity=False)
+            assert h.locations() == [tuple(l) for l in sim.locations]
+            got = h.snapshot()
+            assert set(got) == set(sim.grid.cells)
+            for c, cell in sim.grid.cells.items():
+                media, vel, _ = got[c]
+                assert media == cell.media
+                np.testing.assert_allclose(vel, cell.velocity, rtol=1e-11, atol=1e-12)
+        assert len(got) == 25                              # two rings of air around the marker
+
+
+def test_simulator_mirror_generate_sorts_and_deduplicates_markers():
+    with hb.Simulator() as h:                              # Set.ofList (Simulator.fs:122)
+        h.generate([(30, 0, 0), (0, 0, 0), (30, 0, 0), (0, 10, 0)])
+        assert h.locations() == [(0.0, 0.0, 0.0), (0.0, 10.0, 0.0), (30.0, 0.0, 0.0)]
+        snap = h.snapshot()
+        assert set(snap) == {(0, 0, 0), (0, 10, 0), (30, 0, 0)}
+        assert all(m == hb.FLUID for m, _, _ in snap.values())
