@@ -12,7 +12,7 @@ import os
 from pathlib import Path
 
 LIB_DIR = Path(__file__).resolve().parent / "lib"
-LIB_PATH = LIB_DIR / "libsplashy_cuda.so"
+LIB_PATH = Path(os.environ["SPL_LIB"]) if os.environ.get("SPL_LIB") else LIB_DIR / "libsplashy_cuda.so"
 
 SPL_F32, SPL_F64 = 0, 1
 SPL_PC_NONE, SPL_PC_JACOBI, SPL_PC_RBIC0, SPL_PC_MG = 0, 1, 2, 3

@@ -26,6 +26,14 @@
 
 namespace spl {
 
+#ifndef SPL_MG_RING_D
+#define SPL_MG_RING_D 4
+#endif
+#ifndef SPL_MG_MINB
+#define SPL_MG_MINB 3
+#endif
+constexpr int MG_RING_D = SPL_MG_RING_D;
+
 enum { MG_FIRST2 = 0, MG_PLAIN = 1, MG_PROLONG = 2 };
 enum { MG_SMOOTH = 0, MG_RESTRICT = 1 };
 
@@ -72,7 +80,7 @@ struct alignas(16) MgStage {
 
 template <int MODE, int OUT>
 struct MgSmem {
-  MgStage<MODE> st[RING_D];
+  MgStage<MODE> st[MG_RING_D];
   float4 tile[3][TILE_Y + 2][32];
   float2 rtile[OUT == MG_RESTRICT ? TILE_Y : 1][32];
   double red[32];
@@ -81,7 +89,7 @@ struct MgSmem {
 };
 
 template <int MODE, int OUT, int DOT>
-__global__ void __launch_bounds__(32 * TILE_Y, 3)
+__global__ void __launch_bounds__(32 * TILE_Y, SPL_MG_MINB)
 k_mg_march(const MgMarchArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Smem = MgSmem<MODE, OUT>;
@@ -190,7 +198,7 @@ k_mg_march(const MgMarchArgs p) {
     const float pe = (MODE == MG_PROLONG) ? st.epe[eidx] : 0.f;
     return vcell(st.ea[eidx], c, pe);
   };
-  auto next_slot = [](int s) { return (s + 1 == RING_D) ? 0 : s + 1; };
+  auto next_slot = [](int s) { return (s + 1 == MG_RING_D) ? 0 : s + 1; };
   auto next_tile = [](int t) { return (t + 1 == 3) ? 0 : t + 1; };
 
   // ---- prologue -----------------------------------------------------------------
@@ -198,7 +206,7 @@ k_mg_march(const MgMarchArgs p) {
   float leftc = 0.f, rightc = 0.f;
   long long roff = idx0;
   int rslot = 0;
-  for (int pl = kb; pl < kb + RING_D - 1; ++pl) {
+  for (int pl = kb; pl < kb + MG_RING_D - 1; ++pl) {
     request(pl, rslot, roff);
     roff += plane;
     rslot = next_slot(rslot);
@@ -213,7 +221,7 @@ k_mg_march(const MgMarchArgs p) {
       pe = *reinterpret_cast<const float2*>(p.ec + (long long)((kb - 1) >> 1) * p.cplane + c_own);
     vm = v4(a, c, pe);
   }
-  cp_async_wait<RING_D - 2>();
+  cp_async_wait<MG_RING_D - 2>();
   unsigned codec = 0;
   int tcur = 0;
   if (active) {
@@ -232,7 +240,7 @@ k_mg_march(const MgMarchArgs p) {
   long long idx = idx0;
   int cslot = 0, nslot = 1;
   for (int c = kb; c < ke; ++c, idx += plane) {
-    request(c + RING_D - 1, rslot, roff);
+    request(c + MG_RING_D - 1, rslot, roff);
     roff += plane;
     rslot = next_slot(rslot);
     if (OUT == MG_RESTRICT) {
@@ -241,7 +249,7 @@ k_mg_march(const MgMarchArgs p) {
         ccode = *reinterpret_cast<const unsigned short*>(cc);
       }
     }
-    cp_async_wait<RING_D - 2>();
+    cp_async_wait<MG_RING_D - 2>();
     const int tnext = next_tile(tcur);
     float leftn = 0.f, rightn = 0.f;
     unsigned coden = 0;
