@@ -151,6 +151,7 @@ struct spl_ctx {
   uint8_t* mg_gcodes = nullptr;
   char *mg_gb = nullptr, *mg_gu = nullptr;
   int mg_gsweeps = 100;        // Jacobi sweeps of the global coarsest solve (SPL_MG_GSWEEPS)
+  bool mg_no_fuse = false;     // SPL_MG_NO_FUSE=1: k_phaseB stays a separate launch
   bool mg_no_bottom = false;   // SPL_MG_NO_BOTTOM=1: per-level launches down to the coarsest level
   size_t mg_bottom_smem = 0;
   bool mg_no_march = false;    // SPL_MG_NO_MARCH=1: one-thread-per-cell kernels on every level
@@ -472,7 +473,7 @@ struct Impl {
     zc += zc & 1;                      // even: z pairs of the restriction stay inside a CTA
     return zc;
   }
-  template <int MODE, int OUT, int DOT>
+  template <int MODE, int OUT, int DOT, int RUPD = 0>
   static void mg_march(spl_ctx* c, const MgLevel& l, const char* a, char* out,
                        const MgLevel* coarse, const char* ec, int par, double omega,
                        double omega_v = 0.0) {
@@ -502,19 +503,25 @@ struct Impl {
       p.zchunk = mg_zchunk(l);
       const dim3 grid((l.g.nx + 127) / 128, (l.g.ny + TILE_Y - 1) / TILE_Y,
                       (l.g.nz + p.zchunk - 1) / p.zchunk);
-      using Smem = MgSmem<MODE, OUT>;
-      const int bit = 1 << (MODE * 4 + OUT * 2 + DOT);
+      if (RUPD) {   // level 0: r -= alpha q folded into the pass (replaces k_phaseB)
+        p.q = reinterpret_cast<const float*>(c->q);
+        p.r_out = reinterpret_cast<float*>(c->einv);   // not in place: neighbours still read r
+        p.nsbuf = c->nsbuf;
+      }
+      using Smem = MgSmem<MODE, OUT, RUPD>;
+      const int bit = RUPD ? (1 << 30) : (1 << (MODE * 4 + OUT * 2 + DOT));
       if (!(c->mg_attr_set & bit)) {
-        cudaFuncSetAttribute(k_mg_march<MODE, OUT, DOT>,
+        cudaFuncSetAttribute(k_mg_march<MODE, OUT, DOT, RUPD>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         c->mg_attr_set |= bit;
       }
-      k_mg_march<MODE, OUT, DOT><<<grid, dim3(32, TILE_Y), sizeof(Smem), c->stream>>>(p);
+      k_mg_march<MODE, OUT, DOT, RUPD><<<grid, dim3(32, TILE_Y), sizeof(Smem), c->stream>>>(p);
       c->launches++;
     }
   }
 
-  static int vcycle(spl_ctx* c, int par) {
+  // fuse_r: level 0's first pass also performs the PCG update r -= alpha q (mg_fuse_ok)
+  static int vcycle(spl_ctx* c, int par, bool fuse_r = false) {
     const int L = (int)c->mg.size();
     const int nu = c->mg_nu;
     const std::vector<double>& om = c->mg_omega;   // per-sweep weights (size nu)
@@ -546,6 +553,13 @@ struct Impl {
       if (mg_fast(c, v) && n >= 2) {
         const bool d0 = last && n == 2;
         if (d0) mg_march<MG_FIRST2, MG_SMOOTH, 1>(c, v, v.b, nxt[l], nullptr, nullptr, par, om[1 % nu], om[0]);
+        else if (l == 0 && fuse_r) {
+          // r' = r - alpha q goes to the spare field (SPL_PC_MG does not use einv); the two
+          // buffers then trade places, so every later pass and the next iteration see r'
+          mg_march<MG_FIRST2, MG_SMOOTH, 0, 1>(c, v, v.b, nxt[l], nullptr, nullptr, par, om[1 % nu], om[0]);
+          std::swap(c->r, c->einv);
+          v.b = c->r;
+        }
         else mg_march<MG_FIRST2, MG_SMOOTH, 0>(c, v, v.b, nxt[l], nullptr, nullptr, par, om[1 % nu], om[0]);
         advance_buf(l);
         for (int s = 2; s < n; ++s) {
@@ -683,8 +697,15 @@ struct Impl {
     return xrc;
   }
 
-  static int precondition(spl_ctx* c, int par) {
-    if (c->d.precond == SPL_PC_MG) return vcycle(c, par);
+  // the residual update can ride on the V-cycle's first pass when that pass is the fused
+  // marching kernel on level 0 (fp32, one GPU, at least two levels and two sweeps)
+  static bool mg_fuse_ok(const spl_ctx* c) {
+    return c->d.precond == SPL_PC_MG && std::is_same<T, float>::value && !c->mg_no_fuse &&
+           c->d.world == 1 && c->mg.size() >= 2 && c->mg_nu >= 2 && mg_fast(c, c->mg[0]) &&
+           c->profile_iters == 0;
+  }
+  static int precondition(spl_ctx* c, int par, bool fuse_r = false) {
+    if (c->d.precond == SPL_PC_MG) return vcycle(c, par, fuse_r);
     const Geo& g = c->g;
     const int grid = grid_for(c, g.ncell);
     LAUNCH(c, (k_rb_sweep<T, 1>), grid, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc,
@@ -773,10 +794,12 @@ struct Impl {
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 1], c->stream));
         if ((rc = gather_slots(c, c->sc->gA, 1))) return rc;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 2], c->stream));
-        LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
-               c->sc, c->partials, par, 0, m);
+        const bool fuse_r = (PC == PC_MG) && mg_fuse_ok(c);
+        if (!fuse_r)
+          LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
+                 c->sc, c->partials, par, 0, m);
         if (prof) CU(cudaEventRecord(c->pev[3 * c->profile_iters + (it - 1)], c->stream));
-        if (pc_explicit_z(PC) && (rc = precondition(c, par))) return rc;   // z = M^-1 r, rho = r.z
+        if (pc_explicit_z(PC) && (rc = precondition(c, par, fuse_r))) return rc;   // z = M^-1 r, rho = r.z
         if ((rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
         if (it % m == 0) {   // every buffer holds an unflushed direction: x += sum alpha s
           const bool pf = c->profile_iters > 0 && nflush < 64;
@@ -1074,6 +1097,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
     if (const char* e = getenv("SPL_MG_NO_MARCH")) c->mg_no_march = atoi(e) != 0;
     if (const char* e = getenv("SPL_MG_SUMFORM")) c->mg_sumform = atoi(e) != 0;
     if (const char* e = getenv("SPL_MG_NO_BOTTOM")) c->mg_no_bottom = atoi(e) != 0;
+    if (const char* e = getenv("SPL_MG_NO_FUSE")) c->mg_no_fuse = atoi(e) != 0;
     if (c->mg_nu > MG_MAX_NU) c->mg_nu = MG_MAX_NU;
     // Chebyshev weights for the eigenvalues of D^-1 A in [1/3, 2] (the high-frequency
     // band of the 7-point operator under 2x coarsening), ascending; the post-smoother

@@ -62,11 +62,19 @@ struct MgMarchArgs {
   double* partials;
   int par;                 // rho slot (DOT)
   int zchunk;              // even
+  // RUPD (level 0, MG_FIRST2): the PCG residual update r -= alpha q is folded into this
+  // pass (it replaces k_phaseB): a = r is read together with q, r' is written back
+  const float* q;
+  float* r_out;
+  int nsbuf;
 };
 
-template <int MODE>
+template <int MODE, int RUPD = 0>
 struct alignas(16) MgStage {
   float4 a[256];
+  float4 q[RUPD ? 256 : 1];                    // RUPD: A s of the PCG iteration
+  float4 hq[RUPD ? 64 : 1];
+  float eq[RUPD ? 16 : 1];
   float4 b[MODE == MG_FIRST2 ? 1 : 256];
   float4 ha[64];                               // CTA-edge rows (warp 0: row j-1, warp 7: row j+8)
   unsigned code[256];
@@ -78,21 +86,24 @@ struct alignas(16) MgStage {
   float epe[MODE == MG_PROLONG ? 16 : 1];
 };
 
-template <int MODE, int OUT>
+template <int MODE, int OUT, int RUPD = 0>
 struct MgSmem {
-  MgStage<MODE> st[MG_RING_D];
+  MgStage<MODE, RUPD> st[MG_RING_D];
   float4 tile[3][TILE_Y + 2][32];
   float2 rtile[OUT == MG_RESTRICT ? TILE_Y : 1][32];
   double red[32];
   float wl[8];      // omega / N
   float wv[8];      // omega_v / N
+  double alpha;     // RUPD
 };
 
-template <int MODE, int OUT, int DOT>
+template <int MODE, int OUT, int DOT, int RUPD = 0>
 __global__ void __launch_bounds__(32 * TILE_Y, SPL_MG_MINB)
 k_mg_march(const MgMarchArgs p) {
+  static_assert(!RUPD || (MODE == MG_FIRST2 && OUT == MG_SMOOTH && !DOT), "RUPD is a FIRST2 option");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Smem = MgSmem<MODE, OUT>;
+  using Smem = MgSmem<MODE, OUT, RUPD>;
+  using Stage = MgStage<MODE, RUPD>;
   Smem& sm_ = *reinterpret_cast<Smem*>(smem_raw);
   if (p.sc->done) return;
   const Geo& g = p.g;
@@ -101,7 +112,15 @@ k_mg_march(const MgMarchArgs p) {
     sm_.wl[tid] = (tid >= 1 && tid <= 6) ? p.omega / float(tid) : 0.f;
     sm_.wv[tid] = (tid >= 1 && tid <= 6) ? p.omega_v / float(tid) : 0.f;
   }
+  if (RUPD && tid == 0) {   // alpha of this PCG iteration, exactly as k_phaseB forms it
+    const double rho1 = rho_of(p.sc, p.par ^ 1);
+    const double sq = sum_slots(p.sc->gA, p.sc->world);
+    const double alpha = rho1 / sq;
+    if (linear_block() == 0) p.sc->alpha_hist[(p.sc->count + 1) % p.nsbuf] = alpha;
+    sm_.alpha = alpha;
+  }
   __syncthreads();
+  const float alpha = RUPD ? (float)sm_.alpha : 0.f;
   const float* wl = sm_.wl;
   const float* wv = sm_.wv;
   const bool sumform = p.sumform != 0;
@@ -141,9 +160,10 @@ k_mg_march(const MgMarchArgs p) {
 
   auto request = [&](int pl, int slot, long long off) {
     if (active && pl <= ke) {
-      MgStage<MODE>& st = sm_.st[slot];
+      Stage& st = sm_.st[slot];
       const bool centre = pl < ke;
       cp_async16(&st.a[tid], p.a + off);
+      if (RUPD) cp_async16(&st.q[tid], p.q + off);
       if (MODE != MG_PLAIN || centre) cp_async4(&st.code[tid], p.codes + off);
       long long cpl = 0;
       if (MODE == MG_PROLONG) {
@@ -154,11 +174,13 @@ k_mg_march(const MgMarchArgs p) {
         if (MODE != MG_FIRST2) cp_async16(&st.b[tid], p.b + off);
         if (has_hrow) {
           cp_async16(&st.ha[hidx], p.a + off + hoff);
+          if (RUPD) cp_async16(&st.hq[hidx], p.q + off + hoff);
           if (MODE != MG_PLAIN) cp_async4(&st.hcode[hidx], p.codes + off + hoff);
           if (MODE == MG_PROLONG) cp_async8(&st.hpe[hidx], p.ec + cpl + c_hrow);
         }
         if (has_e) {
           cp_async4(&st.ea[eidx], p.a + off + eoff);
+          if (RUPD) cp_async4(&st.eq[eidx], p.q + off + eoff);
           if (MODE != MG_PLAIN) cp_async4(&st.ecode[eidx], p.codes + ((off + eoff) & ~3LL));
           if (MODE == MG_PROLONG) cp_async4(&st.epe[eidx], p.ec + cpl + c_edge);
         }
@@ -180,23 +202,30 @@ k_mg_march(const MgMarchArgs p) {
     r.w = vcell(a.w, c >> 24, pe.y);
     return r;
   };
+  // RUPD: the operand is the updated residual r - alpha q (same expression as k_phaseB)
+  auto upd4 = [&](float4 a, float4 q) {
+    a.x -= alpha * q.x; a.y -= alpha * q.y; a.z -= alpha * q.z; a.w -= alpha * q.w;
+    return a;
+  };
   auto combine_own = [&](int slot, unsigned& code_out) {
-    const MgStage<MODE>& st = sm_.st[slot];
+    const Stage& st = sm_.st[slot];
     code_out = st.code[tid];
     const float2 pe = (MODE == MG_PROLONG) ? st.pe[tid] : make_float2(0.f, 0.f);
-    return v4(st.a[tid], code_out, pe);
+    return v4(RUPD ? upd4(st.a[tid], st.q[tid]) : st.a[tid], code_out, pe);
   };
   auto combine_hrow = [&](int slot) {
-    const MgStage<MODE>& st = sm_.st[slot];
+    const Stage& st = sm_.st[slot];
     const unsigned c = (MODE != MG_PLAIN) ? st.hcode[hidx] : 0u;
     const float2 pe = (MODE == MG_PROLONG) ? st.hpe[hidx] : make_float2(0.f, 0.f);
-    return v4(st.ha[hidx], c, pe);
+    return v4(RUPD ? upd4(st.ha[hidx], st.hq[hidx]) : st.ha[hidx], c, pe);
   };
   auto combine_edge = [&](int slot) {
-    const MgStage<MODE>& st = sm_.st[slot];
+    const Stage& st = sm_.st[slot];
     const unsigned c = (MODE != MG_PLAIN) ? (st.ecode[eidx] >> eshift) & 0xffu : 0u;
     const float pe = (MODE == MG_PROLONG) ? st.epe[eidx] : 0.f;
-    return vcell(st.ea[eidx], c, pe);
+    float a = st.ea[eidx];
+    if (RUPD) a -= alpha * st.eq[eidx];
+    return vcell(a, c, pe);
   };
   auto next_slot = [](int s) { return (s + 1 == MG_RING_D) ? 0 : s + 1; };
   auto next_tile = [](int t) { return (t + 1 == 3) ? 0 : t + 1; };
@@ -213,7 +242,8 @@ k_mg_march(const MgMarchArgs p) {
   }
   if (active) {                                     // plane kb-1 through registers
     const long long idm = idx0 - plane;
-    const float4 a = *reinterpret_cast<const float4*>(p.a + idm);
+    float4 a = *reinterpret_cast<const float4*>(p.a + idm);
+    if (RUPD) a = upd4(a, *reinterpret_cast<const float4*>(p.q + idm));
     unsigned c = 0u;
     float2 pe = make_float2(0.f, 0.f);
     if (MODE != MG_PLAIN) c = *reinterpret_cast<const unsigned*>(p.codes + idm);
@@ -235,6 +265,8 @@ k_mg_march(const MgMarchArgs p) {
   }
 
   double acc = 0.0;
+  float rmax = 0.f;                                 // RUPD
+  int rbad = 0;
   float zacc0 = 0.f, zacc1 = 0.f;                   // MG_RESTRICT: x-pair sums of the open z pair
   unsigned ccode = 0;                               // codes of the two parents (bytes 0, 1)
   long long idx = idx0;
@@ -272,7 +304,15 @@ k_mg_march(const MgMarchArgs p) {
     if (active) {
       const float4 sym = sm_.tile[tcur][ty][lane];
       const float4 syp = sm_.tile[tcur][ty + 2][lane];
-      const float4 b4 = (MODE == MG_FIRST2) ? sm_.st[cslot].a[tid] : sm_.st[cslot].b[tid];
+      float4 b4 = (MODE == MG_FIRST2) ? sm_.st[cslot].a[tid] : sm_.st[cslot].b[tid];
+      if (RUPD) {   // r' of the own cells: stored, and watched for max |r| / non-finite
+        b4 = upd4(b4, sm_.st[cslot].q[tid]);
+        *reinterpret_cast<float4*>(p.r_out + idx) = b4;
+        const float m4 = fmaxf(fmaxf(fabsf(b4.x), fabsf(b4.y)), fmaxf(fabsf(b4.z), fabsf(b4.w)));
+        rbad |= !(fabsf(b4.x) <= 3.402823466e38f) | !(fabsf(b4.y) <= 3.402823466e38f) |
+                !(fabsf(b4.z) <= 3.402823466e38f) | !(fabsf(b4.w) <= 3.402823466e38f);
+        rmax = fmaxf(rmax, m4);
+      }
       const float s[4] = {vcur.x, vcur.y, vcur.z, vcur.w};
       const float ym[4] = {sym.x, sym.y, sym.z, sym.w};
       const float yp[4] = {syp.x, syp.y, syp.z, syp.w};
@@ -348,6 +388,27 @@ k_mg_march(const MgMarchArgs p) {
   }
   cp_async_wait<0>();
 
+  if (RUPD) {   // max |r| of the iteration into the slot k_phaseB would have filled
+    const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+    const int anybad = __syncthreads_or(rbad);
+    const double bm = block_max((double)rmax, sm_.red);
+    const unsigned nb = num_blocks();
+    if (tid == 0) p.partials[MAX_PARTIALS + linear_block()] = anybad ? kNaN : bm;
+    if (last_block(&p.sc->ticketB, nb)) {
+      double m = 0.0;
+      int nanf = 0;
+      for (unsigned b = tid; b < nb; b += 32 * TILE_Y) {
+        const double v = __ldcg(p.partials + MAX_PARTIALS + b);
+        if (v != v) nanf = 1; else m = fmax(m, v);
+      }
+      nanf = __syncthreads_or(nanf);
+      m = block_max(m, sm_.red);
+      if (tid == 0) {
+        p.sc->gBM[p.par][p.sc->rank][1] = nanf ? kNaN : m;
+        p.sc->count = p.sc->count + 1;
+      }
+    }
+  }
   if (DOT) {
     const double bs = block_sum(acc, sm_.red);
     const unsigned nb = num_blocks();

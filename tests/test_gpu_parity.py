@@ -229,6 +229,25 @@ def test_multigrid_vcycle_matches_oracle(shape, dtype, env, monkeypatch):
     assert np.all(z[lab != dr.FLUID] == 0)
 
 
+def test_multigrid_fused_residual_update_equals_the_separate_phase_b(monkeypatch):
+    """On level 0 the PCG update r -= alpha q rides on the V-cycle's first pass
+    (k_mg_march<FIRST2, ..., RUPD>); SPL_MG_NO_FUSE=1 keeps k_phaseB: same iterates."""
+    sc = scenes.vortex(128, 72, 40, dtype=np.float32)
+    lab, U, V, W = fields(sc, np.float32)
+    res = {}
+    for nofuse in ("0", "1"):
+        monkeypatch.setenv("SPL_MG_NO_FUSE", nofuse)
+        with solver_for(sc, dtype=np.float32, tol=1e-6, precond="mg") as s:
+            s.upload(lab, U, V, W)
+            info = s.project(sc["dt"])
+            res[nofuse] = (info, s.download())
+    (ia, ga), (ib, gb) = res["0"], res["1"]
+    assert ia["converged"] == 1 and ia["iters"] == ib["iters"]
+    assert ia["r_inf"] == ib["r_inf"] and ia["b_inf"] == ib["b_inf"]
+    for n in "UVWP":
+        assert np.array_equal(ga[n], gb[n]), n
+
+
 def test_multigrid_pcg_fp32_dambreak_128():
     sc = scenes.dambreak(128, dtype=np.float32)
     lab, U, V, W = fields(sc, np.float32)
