@@ -243,8 +243,8 @@ def mg_weights(nu: int, omega: Optional[float] = None):
 
 class Multigrid:
     """V(nu, nu) cycle: damped Jacobi with the weights of `mg_weights` (pre-smoother in
-    ascending, post-smoother in descending order -- the cycle stays symmetric), 8-child
-    average restriction, piecewise-constant prolongation, rediscretised operators
+    ascending, post-smoother in descending order -- the cycle stays symmetric), restriction
+    = mean of the children (8 in 3-D, 4 in 2-D), piecewise-constant prolongation, rediscretised operators
     4^-l * L_l and `coarse_sweeps` Jacobi sweeps on the coarsest level (smallest extent
     <= 8).  Restates splashy_b200/csrc/spl_mg.cuh + spl_api.cu Impl::vcycle."""
 
@@ -296,7 +296,8 @@ class Multigrid:
         cz, cy, cx = self.levels[lev + 1]["shape"]
         pad = np.zeros((cz * 2, cy * 2, cx * 2), dtype=self.dtype)
         pad[:r.shape[0], :r.shape[1], :r.shape[2]] = r
-        rc = pad.reshape(cz, 2, cy, 2, cx, 2).sum(axis=(1, 3, 5)) * self.dtype.type(0.125)
+        axes = sum(1 for d in r.shape if d > 1)       # an axis of extent 1 is not coarsened
+        rc = pad.reshape(cz, 2, cy, 2, cx, 2).sum(axis=(1, 3, 5)) * self.dtype.type(0.5 ** axes)
         ec = self.vcycle(rc.astype(self.dtype), lev + 1)
         pe = np.repeat(np.repeat(np.repeat(ec, 2, 0), 2, 1), 2, 2)[:r.shape[0], :r.shape[1],
                                                                   :r.shape[2]]

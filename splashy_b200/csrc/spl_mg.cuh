@@ -22,6 +22,13 @@ namespace spl {
 
 constexpr int MG_MAX_LEVELS = 12;
 
+// restriction = mean of the children: 1 / 2^(number of coarsened axes).  An axis of
+// extent 1 (2-D boxes) is not coarsened, so its "second child" does not exist.
+__host__ __device__ inline double mg_restrict_weight(const Geo& fine) {
+  int axes = (fine.nx > 1) + (fine.ny > 1) + (fine.nz > 1);
+  return axes == 3 ? 0.125 : (axes == 2 ? 0.25 : (axes == 1 ? 0.5 : 1.0));
+}
+
 __device__ __forceinline__ void mg_ijk(const Geo& g, long long idx, int& i, int& j, int& k) {
   i = (int)(idx % g.nx);
   const long long t = idx / g.nx;
@@ -110,7 +117,7 @@ k_mg_restrict(Geo gf, const uint8_t* __restrict__ codes_f, const T* __restrict__
           if (cf & B_FLUID) acc += b[f] - scale * mg_lap<T>(gf, cf, f, u, u[f]);
         }
       }
-      acc *= T(0.125);
+      acc *= T(mg_restrict_weight(gf));
     }
     bc[idx] = acc;
   }
@@ -257,7 +264,7 @@ k_mg_bottom(const MgBottomArgs<T> a) {
             if (cf & B_FLUID) acc += B[l][f] - a.scale[l] * mg_lap_s<T>(gf, cf, f, U[l], U[l][f]);
           }
         }
-        acc *= T(0.125);
+        acc *= T(mg_restrict_weight(gf));
       }
       B[l + 1][idx] = acc;
     }

@@ -23,6 +23,7 @@
 #pragma once
 #include "spl_common.cuh"
 #include "spl_pcg.cuh"
+#include "spl_mg.cuh"
 
 namespace spl {
 
@@ -371,8 +372,9 @@ k_mg_march(const MgMarchArgs p) {
             t.y += u.y;
           }
           float2 r;
-          r.x = (ccode & (unsigned)B_FLUID) ? 0.125f * t.x : 0.f;
-          r.y = ((ccode >> 8) & (unsigned)B_FLUID) ? 0.125f * t.y : 0.f;
+          const float rw = (float)mg_restrict_weight(g);
+          r.x = (ccode & (unsigned)B_FLUID) ? rw * t.x : 0.f;
+          r.y = ((ccode >> 8) & (unsigned)B_FLUID) ? rw * t.y : 0.f;
           *reinterpret_cast<float2*>(p.bc + (long long)(c >> 1) * p.cplane + c_own) = r;
         }
       }
