@@ -96,6 +96,7 @@ struct MgSmem {
   float wl[8];      // omega / N
   float wv[8];      // omega_v / N
   double alpha;     // RUPD
+  unsigned long long bar;   // split-phase barrier of the tile hand-over (spl_pcg.cuh)
 };
 
 template <int MODE, int OUT, int DOT, int RUPD = 0>
@@ -120,6 +121,7 @@ k_mg_march(const MgMarchArgs p) {
     if (linear_block() == 0) p.sc->alpha_hist[(p.sc->count + 1) % p.nsbuf] = alpha;
     sm_.alpha = alpha;
   }
+  if (tid == 0) mbar_init(&sm_.bar, 32 * TILE_Y);
   __syncthreads();
   const float alpha = RUPD ? (float)sm_.alpha : 0.f;
   const float* wl = sm_.wl;
@@ -265,6 +267,9 @@ k_mg_march(const MgMarchArgs p) {
     }
   }
 
+#if SPL_SPLIT_BARRIER
+  mbar_arrive(&sm_.bar);                            // phase 0: tile(kb); see k_phaseA_ring
+#endif
   double acc = 0.0;
   float rmax = 0.f;                                 // RUPD
   int rbad = 0;
@@ -283,6 +288,9 @@ k_mg_march(const MgMarchArgs p) {
       }
     }
     cp_async_wait<MG_RING_D - 2>();
+#if SPL_SPLIT_BARRIER
+    mbar_wait(&sm_.bar, (unsigned)(c - kb) & 1u);
+#endif
     const int tnext = next_tile(tcur);
     float leftn = 0.f, rightn = 0.f;
     unsigned coden = 0;
@@ -297,7 +305,11 @@ k_mg_march(const MgMarchArgs p) {
         }
       }
     }
+#if SPL_SPLIT_BARRIER
+    mbar_arrive(&sm_.bar);
+#else
     __syncthreads();
+#endif
     const float lsh = __shfl_up_sync(0xffffffffu, vcur.w, 1);
     const float rsh = __shfl_down_sync(0xffffffffu, vcur.x, 1);
     const float left = (lane != 0) ? lsh : leftc;

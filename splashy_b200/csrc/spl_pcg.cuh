@@ -346,6 +346,31 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---- split-phase CTA barrier (mbarrier) -------------------------------------------
+// The marching kernels hand the tile of plane c+1 to the neighbouring warps one plane
+// before it is read, so the hand-over does not need a rendezvous: every thread ARRIVES
+// after writing its tile rows and, one iteration later, WAITS for that phase.  Warps
+// drift up to one plane apart instead of meeting at a __syncthreads every plane
+// (barrier stalls were 10-20 % of the issue slots, profiles/).  Hazards: see k_phaseA_ring.
+#ifndef SPL_SPLIT_BARRIER
+#define SPL_SPLIT_BARRIER 1
+#endif
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
+}
+
 struct alignas(16) RingStage {
   float4 a[256];          // z or r of the thread's 4 cells
   float4 old[256];        // previous search direction
@@ -363,6 +388,7 @@ struct RingSmem {
   double red[32];
   float lut[8];
   double beta;
+  unsigned long long bar;   // split-phase barrier of the tile hand-over
   int stop;
 };
 
@@ -378,7 +404,10 @@ k_phaseA_ring(Geo g, const uint8_t* __restrict__ codes, const float* __restrict_
   RingSmem& sm_ = *reinterpret_cast<RingSmem*>(smem_raw);
   const int tid = threadIdx.x + threadIdx.y * 32;
   fill_inv_lut<float>(sm_.lut);
-  if (tid == 0) phaseA_scalars(sc, par, &sm_.stop, &sm_.beta);
+  if (tid == 0) {
+    phaseA_scalars(sc, par, &sm_.stop, &sm_.beta);
+    mbar_init(&sm_.bar, 32 * TILE_Y);
+  }
   __syncthreads();
   if (sm_.stop) return;
 
@@ -509,6 +538,14 @@ k_phaseA_ring(Geo g, const uint8_t* __restrict__ codes, const float* __restrict_
     }
   }
 
+  // Tile hand-over with the split barrier: phase n = "every thread has written its rows
+  // of tile(kb + n)".  Iteration n waits for phase n (so tile(c) is complete, and every
+  // thread has finished iteration n-2, whose tile buffer iteration n overwrites), writes
+  // tile(c+1), arrives for phase n+1, then computes plane c.  A thread can run at most one
+  // tile-write ahead of the slowest one, which the three tile buffers cover.
+#if SPL_SPLIT_BARRIER
+  mbar_arrive(&sm_.bar);                                    // phase 0: tile(kb)
+#endif
   double acc = 0.0;
   long long idx = idx0;
   int nslot = 1;                                            // ring slot of plane c+1
@@ -517,6 +554,9 @@ k_phaseA_ring(Geo g, const uint8_t* __restrict__ codes, const float* __restrict_
     roff += plane;
     rslot = next_slot(rslot);
     cp_async_wait<RING_D - 2>();            // plane c+1 has landed
+#if SPL_SPLIT_BARRIER
+    mbar_wait(&sm_.bar, (unsigned)(c - kb) & 1u);
+#endif
     const int tnext = next_tile(tcur);
     float leftn = 0.f, rightn = 0.f;
     unsigned coden = 0;
@@ -532,7 +572,11 @@ k_phaseA_ring(Geo g, const uint8_t* __restrict__ codes, const float* __restrict_
       }
     }
     nslot = next_slot(nslot);
+#if SPL_SPLIT_BARRIER
+    mbar_arrive(&sm_.bar);
+#else
     __syncthreads();   // tile[tcur] (plane c) was completed before the previous barrier
+#endif
     const float lsh = __shfl_up_sync(0xffffffffu, scur.w, 1);
     const float rsh = __shfl_down_sync(0xffffffffu, scur.x, 1);
     const float left = (lane != 0) ? lsh : leftc;
