@@ -27,6 +27,7 @@
 #include "spl_common.cuh"
 #include "spl_mg.cuh"
 #include "spl_pcg.cuh"
+#include "spl_pcg_ws.cuh"
 #include "spl_mg_march.cuh"
 #include "spl_markers.cuh"
 #include "spl_stencil.cuh"
@@ -160,6 +161,7 @@ struct spl_ctx {
   int ring_attr_set = 0;
   bool no_2d_view = false;     // SPL_NO_2D_VIEW=1: 2-D boxes use the 3-D tiling
   bool no_ring = false;        // SPL_NO_RING=1: force the generic phase-A kernel
+  bool no_ws = false;          // SPL_NO_WS=1: ring kernel without the halo warp (k_phaseA_ring)
   bool no_quad = false;        // SPL_NO_QUAD=1: one-cell-per-thread div / grad / check kernels
   int64_t launches = 0;
   double rhs_dt = 0.0;
@@ -423,6 +425,17 @@ struct Impl {
                             T* snew, int par, int zc) {
     const Geo& g = c->g;
     if constexpr (std::is_same<T, float>::value && VEC == 4) {
+      if (!c->no_ring && !c->no_ws) {   // warp-specialised variant: a ninth warp owns the CTA edges
+        if (!(c->ring_attr_set & (16 << PC))) {
+          cudaFuncSetAttribute(k_phaseA_ws<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(RingSmemWS));
+          c->ring_attr_set |= (16 << PC);
+        }
+        k_phaseA_ws<PC><<<gridA, dim3(32, TILE_Y + 1), sizeof(RingSmemWS), c->stream>>>(
+            g, c->codes, zr, sold, snew, P(c->q), c->sc, c->partials, par, zc);
+        c->launches++;
+        return;
+      }
       if (!c->no_ring) {
         if (!(c->ring_attr_set & (1 << PC))) {   // per context => per device
           cudaFuncSetAttribute(k_phaseA_ring<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1061,6 +1074,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   g.ncell = g.plane * d.nz;
   if (const char* e = getenv("SPL_ZCHUNK")) c->zchunk_override = atoi(e);
   if (const char* e = getenv("SPL_NO_RING")) c->no_ring = atoi(e) != 0;
+  if (const char* e = getenv("SPL_NO_WS")) c->no_ws = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
 

@@ -509,6 +509,35 @@ def test_fixed_iters_and_snapshot_restore():
         assert np.array_equal(ra[n], rb[n])               # deterministic reductions
 
 
+@pytest.mark.parametrize("shape", [(192, 37, 21), (128, 8, 9), (516, 70, 12), (64, 64, 64)])
+def test_phase_a_variants_are_bit_identical(shape, monkeypatch):
+    """k_phaseA_ws (halo warp) and k_phaseA_ring compute the same iterates bit for bit; the
+    generic k_phaseA (different summation order of the dot product) to round-off: fixed 25
+    Jacobi-PCG iterations on a ragged box."""
+    nx, ny, nz = shape
+    sc = scenes.vortex(nx, ny, nz, dtype=np.float32)
+    lab, U, V, W = fields(sc, np.float32)
+    res = []
+    for env in ({}, {"SPL_NO_WS": "1"}, {"SPL_NO_RING": "1"}):
+        for k in ("SPL_NO_WS", "SPL_NO_RING"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with solver_for(sc, dtype=np.float32, tol=1e-6) as s:
+            s.upload(lab, U, V, W)
+            s.set_fixed_iters(25)
+            info = s.project(sc["dt"])
+            res.append((info, s.download()))
+    info, got = res[1]
+    assert info["r_inf"] == res[0][0]["r_inf"]
+    for n in "UVWP":
+        assert np.array_equal(got[n], res[0][1][n]), n
+    info, got = res[2]
+    assert abs(info["r_inf"] - res[0][0]["r_inf"]) <= 1e-5 * res[0][0]["r_inf"]
+    for n in "UVWP":
+        assert np.abs(got[n] - res[0][1][n]).max() <= 1e-5 * vscale(res[0][1][n]), n
+
+
 @pytest.mark.parametrize("shape", [(64, 24, 12), (8, 5, 3), (132, 9, 1)])
 def test_quad_kernels_equal_the_one_cell_kernels_bit_for_bit(shape, monkeypatch):
     """k_div_rhs4 / k_grad_sub4 / k_check4 (fp32, nx % 4 = 0) against the generic kernels
