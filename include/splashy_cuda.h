@@ -196,6 +196,11 @@ int  spl_restore(spl_ctx* ctx);
 /* run exactly `iters` PCG iterations in spl_project / spl_step regardless of
  * tol (0 restores the tolerance-driven loop)                                 */
 int  spl_set_fixed_iters(spl_ctx* ctx, int iters);
+/* iterative refinement of the pressure solve: after PCG has converged on its recursive
+ * residual, r is recomputed as b - A x in fp64 from the fp64 pressure accumulator and
+ * PCG is restarted on it with x kept (`rounds` times; the iterations add up in
+ * spl_info.iters).  Default: 1 for fp32 contexts with SPL_PC_MG, else 0.           */
+int  spl_set_refinement(spl_ctx* ctx, int rounds);
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of
  * this library is launched on): start records an event, stop records a second
  * one, waits for it and returns the elapsed device time in milliseconds.      */

@@ -22,4 +22,5 @@ with Solver(n, n, n, dtype=np.float32, h=sc["h"], rho=sc["rho"], precond="mg", t
     s.restore()
     t = s.step(sc["dt"])
 print(f"n={n} fixed {iters} it: ms_solve {best['ms_solve']:.2f} ({best['ms_solve'] / iters:.3f}/it) "
-      f"ms_total {best['ms_total']:.2f} | to 1e-6: {t['iters']} it, {t['ms_total']:.2f} ms")
+      f"ms_total {best['ms_total']:.2f} | to 1e-6: {t['iters']} it, {t['ms_total']:.2f} ms, "
+      f"max|div| {t['max_abs_div']:.2e}, r_inf/b_inf {t['r_inf'] / t['b_inf']:.2e}")

@@ -93,6 +93,7 @@ SYMBOLS = {
     "spl_snapshot": (C.c_int, [_VP]),
     "spl_restore": (C.c_int, [_VP]),
     "spl_set_fixed_iters": (C.c_int, [_VP, C.c_int]),
+    "spl_set_refinement": (C.c_int, [_VP, C.c_int]),
     "spl_timer_start": (C.c_int, [_VP]),
     "spl_timer_stop": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "spl_profile_pcg": (C.c_int, [_VP, C.c_double, C.c_int, C.POINTER(C.c_float),

@@ -134,6 +134,12 @@ struct spl_ctx {
   ncclComm_t comm = nullptr;
   bool uploaded = false, have_rhs = false, have_snapshot = false;
   int fixed_iters = 0;
+  // iterative refinement: after a converged solve, restart PCG from the true fp64 residual
+  // (k_true_residual) keeping x; default 1 round for fp32 + SPL_PC_MG (SPL_REFINE, spl_set_refinement)
+  int refine_rounds = 0;
+  bool pcg_keep_x = false;
+  double pcg_bmax_keep = 0.0;
+  int iters_base = 0;
   // marker stage
   long long nmark = 0;
   double* mloc = nullptr;      // nmark x 3 locations (metres)
@@ -290,6 +296,7 @@ int pull_scal(spl_ctx* c) {
 }
 
 __global__ void k_set_bmax(Scal* sc) { sc->bmax = rmax_of(sc, 0); }
+__global__ void k_force_bmax(Scal* sc, double v) { sc->bmax = v; }
 
 template <typename A, typename B>
 __global__ void k_convert(long long n, const A* __restrict__ in, B* __restrict__ out) {
@@ -745,7 +752,8 @@ struct Impl {
     // it is written (as s_0 with beta = 0); the halo planes of every buffer are
     // zero from allocation and only ever receive a neighbour slab's planes.
     const int m = c->nsbuf;
-    CU(cudaMemsetAsync(c->alloc[6], 0, field_bytes(c, 8), c->stream));   // p (fp64)
+    if (!c->pcg_keep_x)
+      CU(cudaMemsetAsync(c->alloc[6], 0, field_bytes(c, 8), c->stream));   // p (fp64)
     CU(cudaMemsetAsync(c->sbuf[0] - (size_t)g.hz * g.plane * sizeof(T), 0, fb, c->stream));
     CU(cudaMemsetAsync(c->alloc[10], 0, fb, c->stream));  // q
     SBufs bufs;
@@ -778,6 +786,7 @@ struct Impl {
     if (pc_explicit_z(PC) && (rc = precondition(c, 0))) return rc;
     if ((rc = gather_slots(c, &c->sc->gBM[0][0][0], 2))) return rc;
     LAUNCH(c, k_set_bmax, 1, 1, c->sc);
+    if (c->pcg_keep_x) LAUNCH(c, k_force_bmax, 1, 1, c->sc, c->pcg_bmax_keep);   // refinement pass
     CU(cudaGetLastError());
 
     const int limit = c->fixed_iters > 0 ? c->fixed_iters : c->d.max_iters;
@@ -926,7 +935,7 @@ int read_back(spl_ctx* c, spl_info* info, bool solve, bool chk) {
   const Scal* h = c->hsc;
   if (!info) return SPL_OK;
   if (solve) {
-    info->iters = h->iters;
+    info->iters = h->iters + c->iters_base;
     info->converged = h->converged;
     info->r_inf = h->rmax;
     info->b_inf = h->bmax;
@@ -1073,6 +1082,8 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   g.plane = (long long)d.nx * d.ny;
   g.ncell = g.plane * d.nz;
   if (const char* e = getenv("SPL_ZCHUNK")) c->zchunk_override = atoi(e);
+  c->refine_rounds = (d.dtype == SPL_F32 && d.precond == SPL_PC_MG) ? 1 : 0;
+  if (const char* e = getenv("SPL_REFINE")) c->refine_rounds = atoi(e) > 0 ? atoi(e) : 0;
   if (const char* e = getenv("SPL_NO_RING")) c->no_ring = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_WS")) c->no_ws = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
@@ -1406,7 +1417,30 @@ static int project_impl(spl_ctx* c, double dt, spl_info* info, bool with_advect)
     escapes = c->hsc->escapes;
     too_far = c->d.quirks ? *c->hflag : 0;
   }
+  c->iters_base = 0;
   if ((rc = DISPATCH(c, Impl<float>::pcg_dispatch(c), Impl<double>::pcg_dispatch(c)))) return rc;
+  for (int round = 0; round < c->refine_rounds && c->fixed_iters == 0; ++round) {
+    // iterative refinement: r := b - A x in fp64, PCG restarted on it with x kept
+    if ((rc = pull_scal(c))) return rc;
+    if (!c->hsc->converged || c->hsc->breakdown || !(c->hsc->bmax > 0.0)) break;
+    const double bmax = c->hsc->bmax;
+    const int it0 = c->hsc->iters;
+    if ((rc = do_rhs(c, dt))) return rc;
+    if ((rc = exchange_halo(c, c->p, 8, ncclDouble, 1))) return rc;
+    if (c->d.dtype == SPL_F64)
+      LAUNCH(c, k_true_residual<double>, grid_for(c, c->g.ncell), 256, c->g, c->codes,
+             reinterpret_cast<const double*>(c->p), reinterpret_cast<double*>(c->r));
+    else
+      LAUNCH(c, k_true_residual<float>, grid_for(c, c->g.ncell), 256, c->g, c->codes,
+             reinterpret_cast<const double*>(c->p), reinterpret_cast<float*>(c->r));
+    CU(cudaGetLastError());
+    c->pcg_keep_x = true;
+    c->pcg_bmax_keep = bmax;
+    rc = DISPATCH(c, Impl<float>::pcg_dispatch(c), Impl<double>::pcg_dispatch(c));
+    c->pcg_keep_x = false;
+    if (rc) return rc;
+    c->iters_base += it0;
+  }
   CU(cudaEventRecord(c->ev[3], c->stream));
   if ((rc = DISPATCH(c, Impl<float>::grad(c, dt), Impl<double>::grad(c, dt)))) return rc;
   CU(cudaEventRecord(c->ev[4], c->stream));
@@ -1791,6 +1825,12 @@ int spl_profile_pcg(spl_ctx* c, double dt, int iters, float* ms_a, float* ms_b, 
   delete[] evs;
   c->have_rhs = false;
   return rc;
+}
+
+int spl_set_refinement(spl_ctx* c, int rounds) {
+  if (!c || rounds < 0 || rounds > 8) return SPL_E_BADARG;
+  c->refine_rounds = rounds;
+  return SPL_OK;
 }
 
 int spl_set_fixed_iters(spl_ctx* c, int iters) {

@@ -322,6 +322,36 @@ k_check4(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ u,
   }
 }
 
+// ---- true residual (iterative refinement of the fp32 solve) -----------------------------
+// r = b - A x with x the fp64 pressure accumulator and the stencil evaluated in fp64:
+// the recursive residual of PCG drifts from the true one by ~eps32 |A| |x| (the search
+// directions are fp32), which is what limits the divergence-free residual of a solve that
+// converges in a few large steps (multigrid).  One restart from this residual removes it.
+// In place: r holds b on entry.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_true_residual(Geo g, const uint8_t* __restrict__ codes, const double* __restrict__ x,
+                T* __restrict__ r) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const unsigned c = codes[idx];
+    T out = T(0);
+    if (c & B_FLUID) {
+      const double x0 = x[idx];
+      double sum = 0.0;
+      // Air neighbours carry p = 0 (Constants.fs:20) and x is 0 on every non-Fluid cell
+      if (c & B_XM) sum += x[idx - 1];
+      if (c & B_XP) sum += x[idx + 1];
+      if (c & B_YM) sum += x[idx - g.nx];
+      if (c & B_YP) sum += x[idx + g.nx];
+      if (c & B_ZM) sum += x[idx - g.plane];
+      if (c & B_ZP) sum += x[idx + g.plane];
+      out = (T)((double)r[idx] - ((double)__popc(c & 63u) * x0 - sum));
+    }
+    r[idx] = out;
+  }
+}
+
 // ---- forces ---------------------------------------------------------------------
 // Forces.fs:6-12: v += gravity * dt on every Fluid cell.
 template <typename T>

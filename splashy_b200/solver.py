@@ -210,6 +210,10 @@ class Solver:
     def timer_start(self):
         self._check(self._lib.spl_timer_start(self._ctx))
 
+    def set_refinement(self, rounds: int) -> None:
+        """Rounds of iterative refinement (true fp64 residual + PCG restart) per solve."""
+        self._check(self._lib.spl_set_refinement(self._ctx, rounds))
+
     def timer_stop(self) -> float:
         ms = C.c_float()
         self._check(self._lib.spl_timer_stop(self._ctx, C.byref(ms)))
