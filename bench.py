@@ -66,7 +66,7 @@ def ncu_traffic(kernel: str, n: int):
         return None
     try:
         t = json.loads(p.read_text())
-        key = "k_phaseA_ring" if kernel == "k_phaseA" else kernel
+        key = "k_phaseA_ws" if kernel == "k_phaseA" else kernel
         return float(t[key]["dram_bytes"])
     except Exception:
         return None
