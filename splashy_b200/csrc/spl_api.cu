@@ -138,8 +138,10 @@ struct spl_ctx {
   // (k_true_residual) keeping x; default 1 round for fp32 + SPL_PC_MG (SPL_REFINE, spl_set_refinement)
   int refine_rounds = 0;
   bool pcg_keep_x = false;
+  double pcg_tol_first = 0.0;  // > 0: stopping tolerance of the pass before a refinement round
   double pcg_bmax_keep = 0.0;
   int iters_base = 0;
+  double refine_first_tol = 1e-4;   // SPL_REFINE_FIRST_TOL
   // marker stage
   long long nmark = 0;
   double* mloc = nullptr;      // nmark x 3 locations (metres)
@@ -764,7 +766,7 @@ struct Impl {
     memset(h, 0, sizeof(Scal));
     h->world = c->d.world;
     h->rank = c->d.rank;
-    h->tol = c->fixed_iters > 0 ? 0.0 : c->d.tol;
+    h->tol = c->fixed_iters > 0 ? 0.0 : (c->pcg_tol_first > 0.0 ? c->pcg_tol_first : c->d.tol);
     h->nonfinite = keep_nf;
     for (int w = 0; w < c->d.world; ++w)
       h->gBM[1][w][0] = (w == 0) ? std::numeric_limits<double>::infinity() : 0.0;
@@ -1084,6 +1086,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if (const char* e = getenv("SPL_ZCHUNK")) c->zchunk_override = atoi(e);
   c->refine_rounds = (d.dtype == SPL_F32 && d.precond == SPL_PC_MG) ? 1 : 0;
   if (const char* e = getenv("SPL_REFINE")) c->refine_rounds = atoi(e) > 0 ? atoi(e) : 0;
+  if (const char* e = getenv("SPL_REFINE_FIRST_TOL")) c->refine_first_tol = atof(e);
   if (const char* e = getenv("SPL_NO_RING")) c->no_ring = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_WS")) c->no_ws = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
@@ -1418,7 +1421,14 @@ static int project_impl(spl_ctx* c, double dt, spl_info* info, bool with_advect)
     too_far = c->d.quirks ? *c->hflag : 0;
   }
   c->iters_base = 0;
-  if ((rc = DISPATCH(c, Impl<float>::pcg_dispatch(c), Impl<double>::pcg_dispatch(c)))) return rc;
+  // with a refinement round to follow, the first pass only needs to reach the level where
+  // the fp32 recursive residual stops tracking the true one (~1e-4 max|b| on large grids);
+  // the restart from the fp64 residual does the rest
+  const bool refine = c->refine_rounds > 0 && c->fixed_iters == 0;
+  c->pcg_tol_first = (refine && c->d.tol < c->refine_first_tol) ? c->refine_first_tol : 0.0;
+  rc = DISPATCH(c, Impl<float>::pcg_dispatch(c), Impl<double>::pcg_dispatch(c));
+  c->pcg_tol_first = 0.0;
+  if (rc) return rc;
   for (int round = 0; round < c->refine_rounds && c->fixed_iters == 0; ++round) {
     // iterative refinement: r := b - A x in fp64, PCG restarted on it with x kept
     if ((rc = pull_scal(c))) return rc;
