@@ -48,6 +48,7 @@ __global__ void k_move_markers(Geo g, const uint8_t* __restrict__ media,
                                long long n, double dt, int h, int ox, int oy, int oz,
                                int sum_faces, long long* __restrict__ old_cell,
                                long long* __restrict__ new_cell, MarkerStats* st) {
+  unsigned n_out = 0, n_moved = 0;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n;
        m += (long long)gridDim.x * blockDim.x) {
     double l[3] = {loc[3 * m], loc[3 * m + 1], loc[3 * m + 2]};
@@ -55,7 +56,7 @@ __global__ void k_move_markers(Geo g, const uint8_t* __restrict__ media,
     old_cell[m] = idx;
     if (idx < 0) {
       new_cell[m] = -1;
-      atomicAdd(&st->outside, 1ull);
+      ++n_out;
       continue;
     }
     const int i = (int)(idx % g.nx);
@@ -75,8 +76,15 @@ __global__ void k_move_markers(Geo g, const uint8_t* __restrict__ media,
     }
     const long long nidx = marker_cell(g, l, h, ox, oy, oz);
     new_cell[m] = nidx;
-    if (nidx < 0) atomicAdd(&st->outside, 1ull);
-    else if (nidx != idx) atomicAdd(&st->moved, 1ull);
+    n_out += (nidx < 0);
+    n_moved += (nidx >= 0 && nidx != idx);
+  }
+  // one atomic per warp (millions of markers move every step)
+  n_out = __reduce_add_sync(0xffffffffu, n_out);
+  n_moved = __reduce_add_sync(0xffffffffu, n_moved);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_out) atomicAdd(&st->outside, (unsigned long long)n_out);
+    if (n_moved) atomicAdd(&st->moved, (unsigned long long)n_moved);
   }
 }
 
