@@ -76,12 +76,39 @@ __device__ __forceinline__ T mix(T a, T b, T w) {   // (1 - w) a + w b
 
 // unchecked trilinear sample at (cell + offset); p0 = address of the cell's own
 // value, nx / pl = element strides (pl < 2^31 is guaranteed by the host)
+// floor + float->int of a small offset.  -DSPL_ADV_MAGIC=1 avoids the conversion pipe (FRND /
+// F2I issue at 16 lanes/clk/SM, the hot kernel needs 54 per cell) by adding 1.5 * 2^23, which
+// leaves round-to-nearest(o - 1/2) in the low mantissa bits; measured SLOWER at 512^3 (4.79 vs
+// 4.68 ms: 784 instead of 744 instructions per cell -- the kernel is issue-bound, the
+// conversion pipe is not the limiter), so it is off.
+#ifndef SPL_ADV_MAGIC
+#define SPL_ADV_MAGIC 0
+#endif
+__device__ __forceinline__ void floor_split(float o, float& f, int& i) {
+#if SPL_ADV_MAGIC
+  const float t = (o - 0.5f) + 12582912.0f;
+  i = __float_as_int(t) - 0x4B400000;
+  f = t - 12582912.0f;
+#else
+  f = floorf(o);
+  i = (int)f;
+#endif
+}
+__device__ __forceinline__ void floor_split(double o, double& f, int& i) {
+  f = floor(o);
+  i = (int)f;
+}
+
 template <typename T>
 __device__ __forceinline__ T sample_fast(const T* __restrict__ p0, int nx, int pl, T ox, T oy,
                                          T oz) {
-  const T fx = floor(ox), fy = floor(oy), fz = floor(oz);
+  T fx, fy, fz;
+  int ix, iy, iz;
+  floor_split(ox, fx, ix);
+  floor_split(oy, fy, iy);
+  floor_split(oz, fz, iz);
   const T wx = ox - fx, wy = oy - fy, wz = oz - fz;
-  const int off = ((int)fz * pl + (int)fy * nx) + (int)fx;
+  const int off = (iz * pl + iy * nx) + ix;
   const T* __restrict__ pa = p0 + off;
   const T* __restrict__ pb = pa + pl;
   const T A = mix(mix(pa[0], pa[1], wx), mix(pa[nx], pa[nx + 1], wx), wy);
