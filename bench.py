@@ -36,7 +36,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "advect+project cell-updates/s"
 UNIT = "cell-updates/s"
-NSBUF = int(os.environ.get("SPL_NSBUF", "8"))   # x is flushed every NSBUF iterations
+NSBUF = int(os.environ.get("SPL_NSBUF", "16"))   # x is flushed every NSBUF iterations
 BYTES_PHASE_A = 17     # r 4 + s 4 + code 1 -> s' 4 + q 4                 
 BYTES_PHASE_B = 13     # r 4 + q 4 + code 1 -> r 4  (Jacobi)
 BYTES_XFLUSH = 4 * NSBUF + 16   # per launch: NSBUF directions + fp64 x read / write

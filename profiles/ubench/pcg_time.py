@@ -3,8 +3,11 @@ python profiles/ubench/pcg_time.py [n] ; SPL_LIB=<variant .so> selects another b
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
+import os
 import numpy as np
 from splashy_b200 import Solver, scenes
+
+M = int(os.environ.get("SPL_NSBUF", "16"))
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 sc = scenes.vortex(n, n, n, dtype=np.float32)
@@ -19,4 +22,4 @@ with Solver(n, n, n, dtype=np.float32, h=sc["h"], rho=sc["rho"], precond="jacobi
 a, b, x = best
 cells = n ** 3
 print(f"n={n} phaseA {a:.4f} ms ({cells * 17 / a / 1e6:.0f} GB/s)  phaseB {b:.4f} ms ({cells * 13 / b / 1e6:.0f} GB/s)  "
-      f"xflush {x:.4f} ms  iteration {a + b + x / 8:.4f} ms")
+      f"xflush {x:.4f} ms (every {M})  iteration {a + b + x / M:.4f} ms")

@@ -115,13 +115,13 @@ struct spl_ctx {
   int profile_flushes = 0;
   int profile_iters = 0;       // > 0 while spl_profile_pcg runs
   // fields, allocation start (plane -hz); *_0 = plane 0
-  void* alloc[32]{};
+  void* alloc[64]{};
   char *u = nullptr, *v = nullptr, *w = nullptr;     // current velocity (plane 0)
   char *u2 = nullptr, *v2 = nullptr, *w2 = nullptr;  // advection target
   char *su = nullptr, *sv = nullptr, *sw = nullptr;  // snapshot
   char *p = nullptr, *r = nullptr, *q = nullptr;
   char* sbuf[MAX_SBUF]{};      // ring of search-direction buffers (plane 0 pointers)
-  int nsbuf = 8;               // m: x is updated every m iterations (SPL_NSBUF)
+  int nsbuf = 16;              // m: x is updated every m iterations (SPL_NSBUF)
   char *z = nullptr, *einv = nullptr;
   uint8_t *media = nullptr, *codes = nullptr, *layer = nullptr;
   Scal* sc = nullptr;          // device
@@ -1108,7 +1108,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if (c->nsbuf < 2) c->nsbuf = 2;
   if (c->nsbuf > MAX_SBUF) c->nsbuf = MAX_SBUF;
   for (int i = 0; i < c->nsbuf; ++i)
-    if ((rc = alloc_field(c, 16 + i, c->esz, &c->sbuf[i], 0))) return rc;
+    if ((rc = alloc_field(c, 32 + i, c->esz, &c->sbuf[i], 0))) return rc;
   if (d.precond == SPL_PC_RBIC0 || d.precond == SPL_PC_MG) {
     if ((rc = alloc_field(c, 11, c->esz, &c->z, 0))) return rc;
     if ((rc = alloc_field(c, 12, c->esz, &c->einv, 0))) return rc;

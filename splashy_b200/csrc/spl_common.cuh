@@ -23,7 +23,7 @@ constexpr int B_XM = 1, B_XP = 2, B_YM = 4, B_YP = 8, B_ZM = 16, B_ZP = 32,
 constexpr int MAXW = 16;       // max ranks (z-slabs)
 constexpr int TILE_Y = 8;      // rows per CTA in the marching stencil kernels
 constexpr int MAX_PARTIALS = 1 << 16;
-constexpr int MAX_SBUF = 8;    // ring of search-direction buffers (deferred x update)
+constexpr int MAX_SBUF = 16;   // ring of search-direction buffers (deferred x update)
 
 struct Geo {
   int nx, ny, nz;      // local box
