@@ -136,6 +136,7 @@ class ClockSampler:
 def cpu_sample(n: int, pcg_iters: int, repeats: int = 1):
     from oracle import c_port
     from splashy_b200 import scenes
+    c_port.use_all_cores()
     sc = scenes.vortex(n, n, n, dtype=np.float32)
     best = None
     for _ in range(repeats):
@@ -159,6 +160,7 @@ def run_reference(args):
     n = args.cpu_n
     from oracle import c_port
     from splashy_b200 import scenes
+    c_port.use_all_cores()          # torchrun exports OMP_NUM_THREADS=1 to the ranks
     sc = scenes.vortex(n, n, n, dtype=np.float32)
     times = []
     for i in range(args.warmup + args.steps):

@@ -25,6 +25,7 @@ def load():
         subprocess.run(["make", "-C", str(HERE)], check=True)
     lib = C.CDLL(str(LIB))
     lib.orc_threads.restype = C.c_int
+    lib.orc_set_threads.argtypes = [C.c_int]
     lib.orc_codes.argtypes = [C.c_int] * 3 + [_u8p, _u8p]
     lib.orc_div_rhs.argtypes = [C.c_int] * 3 + [_u8p, _f32p, _f32p, _f32p, C.c_float, _f32p]
     lib.orc_pcg_jacobi.restype = C.c_int
@@ -44,6 +45,17 @@ def load():
 
 def threads() -> int:
     return int(load().orc_threads())
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    load().orc_set_threads(n)
+    return threads()
 
 
 def advect(labels, U, V, W, dt, h):

@@ -40,6 +40,16 @@ int orc_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed CPU arm asks for the
+ * host's cores explicitly */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* Pressure.fs:34-38,42-43,53 */
 void orc_codes(int nx, int ny, int nz, const uint8_t* lab, uint8_t* codes) {
   const int64_t plane = (int64_t)nx * ny;
