@@ -1182,7 +1182,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
       gg.nz = k.nzg; gg.z0 = 0; gg.ncell = gg.plane * gg.nz;
       const bool equal = (long long)k.nz * d.world == k.nzg && k.z0 == d.rank * k.nz;
       const size_t smem = (size_t)gg.ncell * (3 * c->esz + 1) + 64;
-      if (equal && smem <= 200 * 1024) {
+      if (equal && smem <= 216 * 1024) {
         c->mg_gbottom = true;
         c->mg_gg = gg;
         CU(cudaMalloc(&c->mg_gcodes, (size_t)gg.ncell));
