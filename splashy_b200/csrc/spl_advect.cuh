@@ -66,7 +66,9 @@ __device__ __forceinline__ T sample(const FieldView<T>& F, int bi, int bj, int b
 // ends), one dense thread per listed cell.  The hot kernel is
 // instruction-issue / L1-gather bound, not HBM bound: it is
 // written for instruction count (32-bit offsets, lerp form, no calls, no stack).
-constexpr int ADV_MARGIN = 4;      // x / y cells from the box edge
+// x / y cells from the box edge: with every offset (incl. the +-1/2 staggering shifts) inside
+// [-2.99, 2.99], floor() is in [-3, 2] and the corners span [-3, +3]
+constexpr int ADV_MARGIN = 3;
 constexpr float ADV_MAXOFF = 2.99f;
 
 template <typename T>
