@@ -404,6 +404,35 @@ def test_advect_fp32_within_1e5_relative(name):
         assert np.abs(got[n] - r).max() <= 1e-5 * vs, n   # north_star tolerance
 
 
+@pytest.mark.parametrize("cfl", [(2.9, -2.9, 2.9), (-2.95, 2.95, -2.95), (2.4, 2.4, -2.4),
+                                 (-0.3, 2.97, 0.1)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_advect_large_offsets_next_to_the_box_faces(cfl, dtype):
+    """Backtraces of almost 3 cells in every direction on a box without a solid shell: the
+    fast path (cells >= 3 from the x / y faces, footprint [-3, +3]) and the bounds-tested
+    worklist path meet exactly where the footprint would leave the box; corners outside the
+    box read as 0 (Convection.fs:36-38)."""
+    nx, ny, nz = 24, 20, 16
+    rng = np.random.default_rng(2)
+    h, dt = 10.0, 1.0
+    lab = np.full((nz, ny, nx), dr.FLUID, dtype=np.uint8)
+    U = (cfl[0] * h / dt + rng.uniform(-0.2, 0.2, lab.shape)).astype(dtype)
+    V = (cfl[1] * h / dt + rng.uniform(-0.2, 0.2, lab.shape)).astype(dtype)
+    W = (cfl[2] * h / dt + rng.uniform(-0.2, 0.2, lab.shape)).astype(dtype)
+    with Solver(nx, ny, nz, dtype=dtype, h=h) as s:
+        s.upload(lab, U, V, W)
+        try:
+            s.advect(dt)
+        except SplashyError:
+            pass                       # z departures beyond the single-GPU halo are reported
+        got = s.download()
+    want = dr.advect(lab, U.astype(np.float64), V.astype(np.float64), W.astype(np.float64), dt, h)
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    inner = (slice(4, -4),)            # planes whose z footprint stays inside the box + halo
+    for n, r in zip("UVW", want):
+        assert np.abs(got[n][inner] - r[inner]).max() <= tol * vscale(*want), n
+
+
 def test_quirk_mode_reproduces_the_reference_trace():
     """SPL_Q_* = 7: forward RK2 trace + nearest-cell whole-vector copy with the
     reference's index-snap interpolation (Convection.fs:21-66), on a state where
