@@ -28,6 +28,7 @@
 #include "spl_mg.cuh"
 #include "spl_pcg.cuh"
 #include "spl_pcg_ws.cuh"
+#include "spl_pcg_tma.cuh"
 #include "spl_mg_march.cuh"
 #include "spl_markers.cuh"
 #include "spl_stencil.cuh"
@@ -169,6 +170,10 @@ struct spl_ctx {
   int ring_attr_set = 0;
   bool no_2d_view = false;     // SPL_NO_2D_VIEW=1: 2-D boxes use the 3-D tiling
   bool no_ring = false;        // SPL_NO_RING=1: force the generic phase-A kernel
+  // TMA phase A (default when nx % 16 = 0; SPL_TMA=0 disables): tensor maps per field, keyed by
+  // the field's plane-0 pointer
+  bool use_tma = true;
+  std::vector<std::pair<const void*, CUtensorMap>> tmaps;
   bool no_ws = false;          // SPL_NO_WS=1: ring kernel without the halo warp (k_phaseA_ring)
   bool no_quad = false;        // SPL_NO_QUAD=1: one-cell-per-thread div / grad / check kernels
   int64_t launches = 0;
@@ -334,6 +339,44 @@ int phaseA_zchunk(const spl_ctx* c, int tiles_xy) {
   return zc;
 }
 
+// ---- TMA tensor maps (k_phaseA_tma) -------------------------------------------------------
+// A field is described as a rank-3 tensor (x fastest) over its whole allocation, halo planes
+// included (z coordinate = plane + hz); the box is the raw tile of one CTA and one plane.
+// cuTensorMapEncodeTiled is fetched from the driver at run time (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+const CUtensorMap* tensor_map_for(spl_ctx* c, const void* plane0, bool is_codes) {
+  for (auto& kv : c->tmaps)
+    if (kv.first == plane0) return &kv.second;
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
+            cudaSuccess || !fn)
+      return nullptr;
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const Geo& g = c->g;
+  const size_t es = is_codes ? 1 : 4;
+  char* base = static_cast<char*>(const_cast<void*>(plane0)) - (size_t)g.hz * g.plane * es;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)(g.nz + 2 * g.hz)};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.nx * es, (cuuint64_t)g.plane * es};
+  const cuuint32_t box[3] = {(cuuint32_t)(is_codes ? TMA_CX : TMA_BX), (cuuint32_t)TMA_BY, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUtensorMap m;
+  const CUresult r = encode(&m, is_codes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                            3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return nullptr;
+  c->tmaps.emplace_back(plane0, m);
+  return &c->tmaps.back().second;
+}
+
 // ---- typed implementation -------------------------------------------------------
 template <typename T>
 struct Impl {
@@ -434,6 +477,24 @@ struct Impl {
                             T* snew, int par, int zc) {
     const Geo& g = c->g;
     if constexpr (std::is_same<T, float>::value && VEC == 4) {
+      if (c->use_tma && !c->no_ring && !c->no_ws && g.nx % 16 == 0) {   // TMA producer warp
+        c->tmaps.reserve(64);             // pointers into the vector stay valid
+        const CUtensorMap* mz = tensor_map_for(c, zr, false);
+        const CUtensorMap* mo = tensor_map_for(c, sold, false);
+        const CUtensorMap* mn = tensor_map_for(c, snew, false);
+        const CUtensorMap* mc = tensor_map_for(c, c->codes, true);
+        if (mz && mo && mn && mc) {
+          if (!(c->ring_attr_set & (256 << PC))) {
+            cudaFuncSetAttribute(k_phaseA_tma<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(TmaSmem));
+            c->ring_attr_set |= (256 << PC);
+          }
+          k_phaseA_tma<PC><<<gridA, dim3(32, TILE_Y + 1), sizeof(TmaSmem), c->stream>>>(
+              *mz, *mo, *mn, *mc, g, c->codes, zr, sold, snew, P(c->q), c->sc, c->partials, par, zc);
+          c->launches++;
+          return;
+        }
+      }
       if (!c->no_ring && !c->no_ws) {   // warp-specialised variant: a ninth warp owns the CTA edges
         if (!(c->ring_attr_set & (16 << PC))) {
           cudaFuncSetAttribute(k_phaseA_ws<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1089,6 +1150,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if (const char* e = getenv("SPL_REFINE_FIRST_TOL")) c->refine_first_tol = atof(e);
   if (const char* e = getenv("SPL_NO_RING")) c->no_ring = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_WS")) c->no_ws = atoi(e) != 0;
+  if (const char* e = getenv("SPL_TMA")) c->use_tma = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
 

@@ -587,15 +587,16 @@ def test_thin_boxes_fp32_project_matches_oracle(shape, precond):
 
 @pytest.mark.parametrize("shape", [(192, 37, 21), (128, 8, 9), (516, 70, 12), (64, 64, 64)])
 def test_phase_a_variants_are_bit_identical(shape, monkeypatch):
-    """k_phaseA_ws (halo warp) and k_phaseA_ring compute the same iterates bit for bit; the
+    """k_phaseA_tma (TMA producer warp, the default when nx % 16 = 0), k_phaseA_ws (halo warp)
+    and k_phaseA_ring compute the same iterates bit for bit; the
     generic k_phaseA (different summation order of the dot product) to round-off: fixed 25
     Jacobi-PCG iterations on a ragged box."""
     nx, ny, nz = shape
     sc = scenes.vortex(nx, ny, nz, dtype=np.float32)
     lab, U, V, W = fields(sc, np.float32)
     res = []
-    for env in ({}, {"SPL_NO_WS": "1"}, {"SPL_NO_RING": "1"}):
-        for k in ("SPL_NO_WS", "SPL_NO_RING"):
+    for env in ({"SPL_TMA": "0"}, {"SPL_NO_WS": "1"}, {"SPL_NO_RING": "1"}, {"SPL_TMA": "1"}):
+        for k in ("SPL_NO_WS", "SPL_NO_RING", "SPL_TMA"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -605,6 +606,10 @@ def test_phase_a_variants_are_bit_identical(shape, monkeypatch):
             info = s.project(sc["dt"])
             res.append((info, s.download()))
     info, got = res[1]
+    assert info["r_inf"] == res[0][0]["r_inf"]
+    for n in "UVWP":
+        assert np.array_equal(got[n], res[0][1][n]), n
+    info, got = res[3]                                   # TMA producer warp (nx % 16 = 0)
     assert info["r_inf"] == res[0][0]["r_inf"]
     for n in "UVWP":
         assert np.array_equal(got[n], res[0][1][n]), n
