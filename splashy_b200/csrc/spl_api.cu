@@ -29,6 +29,7 @@
 #include "spl_pcg.cuh"
 #include "spl_pcg_ws.cuh"
 #include "spl_pcg_tma.cuh"
+#include "spl_mg_tma.cuh"
 #include "spl_mg_march.cuh"
 #include "spl_markers.cuh"
 #include "spl_stencil.cuh"
@@ -174,6 +175,9 @@ struct spl_ctx {
   // the field's plane-0 pointer
   bool use_tma = true;
   std::vector<std::pair<const void*, CUtensorMap>> tmaps;
+  std::vector<int> tmap_kind;
+  bool mg_no_tma = false;      // SPL_MG_TMA=0: multigrid passes with per-thread cp.async (k_mg_march)
+  int mgt_attr_set = 0;
   bool no_ws = false;          // SPL_NO_WS=1: ring kernel without the halo warp (k_phaseA_ring)
   bool no_quad = false;        // SPL_NO_QUAD=1: one-cell-per-thread div / grad / check kernels
   int64_t launches = 0;
@@ -348,9 +352,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-const CUtensorMap* tensor_map_for(spl_ctx* c, const void* plane0, bool is_codes) {
+enum { TM_F = 0, TM_C = 1, TM_E = 2 };   // fp32 raw tile, u8 code tile, coarse-correction tile
+
+const CUtensorMap* tensor_map_for(spl_ctx* c, const Geo& g, const void* plane0, int kind) {
   for (auto& kv : c->tmaps)
-    if (kv.first == plane0) return &kv.second;
+    if (kv.first == plane0 && c->tmap_kind[&kv - &c->tmaps[0]] == kind) return &kv.second;
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -360,12 +366,15 @@ const CUtensorMap* tensor_map_for(spl_ctx* c, const void* plane0, bool is_codes)
       return nullptr;
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  const Geo& g = c->g;
+  if (c->tmaps.size() >= c->tmaps.capacity()) return nullptr;   // pointers handed out must stay valid
+  const bool is_codes = kind == TM_C;
   const size_t es = is_codes ? 1 : 4;
   char* base = static_cast<char*>(const_cast<void*>(plane0)) - (size_t)g.hz * g.plane * es;
   const cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)(g.nz + 2 * g.hz)};
   const cuuint64_t strides[2] = {(cuuint64_t)g.nx * es, (cuuint64_t)g.plane * es};
-  const cuuint32_t box[3] = {(cuuint32_t)(is_codes ? TMA_CX : TMA_BX), (cuuint32_t)TMA_BY, 1u};
+  cuuint32_t box[3] = {(cuuint32_t)TMA_BX, (cuuint32_t)TMA_BY, 1u};
+  if (kind == TM_C) box[0] = TMA_CX;
+  if (kind == TM_E) { box[0] = MGT_EX; box[1] = MGT_EY; }
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   CUtensorMap m;
   const CUresult r = encode(&m, is_codes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
@@ -374,6 +383,7 @@ const CUtensorMap* tensor_map_for(spl_ctx* c, const void* plane0, bool is_codes)
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return nullptr;
   c->tmaps.emplace_back(plane0, m);
+  c->tmap_kind.push_back(kind);
   return &c->tmaps.back().second;
 }
 
@@ -478,11 +488,10 @@ struct Impl {
     const Geo& g = c->g;
     if constexpr (std::is_same<T, float>::value && VEC == 4) {
       if (c->use_tma && !c->no_ring && !c->no_ws && g.nx % 16 == 0) {   // TMA producer warp
-        c->tmaps.reserve(64);             // pointers into the vector stay valid
-        const CUtensorMap* mz = tensor_map_for(c, zr, false);
-        const CUtensorMap* mo = tensor_map_for(c, sold, false);
-        const CUtensorMap* mn = tensor_map_for(c, snew, false);
-        const CUtensorMap* mc = tensor_map_for(c, c->codes, true);
+        const CUtensorMap* mz = tensor_map_for(c, g, zr, TM_F);
+        const CUtensorMap* mo = tensor_map_for(c, g, sold, TM_F);
+        const CUtensorMap* mn = tensor_map_for(c, g, snew, TM_F);
+        const CUtensorMap* mc = tensor_map_for(c, g, c->codes, TM_C);
         if (mz && mo && mn && mc) {
           if (!(c->ring_attr_set & (256 << PC))) {
             cudaFuncSetAttribute(k_phaseA_tma<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -590,6 +599,28 @@ struct Impl {
         p.q = reinterpret_cast<const float*>(c->q);
         p.r_out = reinterpret_cast<float*>(c->einv);   // not in place: neighbours still read r
         p.nsbuf = c->nsbuf;
+      }
+      if (c->use_tma && !c->mg_no_tma && l.g.nx % 16 == 0 &&
+          (MODE != MG_PROLONG || (coarse->g.nx % 4 == 0 && coarse->g.hz == 1))) {
+        // TMA producer warp (spl_mg_tma.cuh): one tensor map per field of the level
+        const CUtensorMap* ma = tensor_map_for(c, l.g, a, TM_F);
+        const CUtensorMap* mb = tensor_map_for(c, l.g, RUPD ? c->q : l.b, TM_F);
+        const CUtensorMap* mc = tensor_map_for(c, l.g, l.codes, TM_C);
+        const CUtensorMap* me = (MODE == MG_PROLONG) ? tensor_map_for(c, coarse->g, ec, TM_E) : ma;
+        if (ma && mb && mc && me) {
+          MgTmaMaps tm;
+          tm.a = *ma; tm.b = *mb; tm.code = *mc; tm.ec = *me;
+          using SmemT = MgtSmem<MODE, OUT, RUPD>;
+          const int tbit = RUPD ? (1 << 30) : (1 << (MODE * 4 + OUT * 2 + DOT));
+          if (!(c->mgt_attr_set & tbit)) {
+            cudaFuncSetAttribute(k_mg_tma<MODE, OUT, DOT, RUPD>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT));
+            c->mgt_attr_set |= tbit;
+          }
+          k_mg_tma<MODE, OUT, DOT, RUPD><<<grid, dim3(32, TILE_Y + 1), sizeof(SmemT), c->stream>>>(tm, p);
+          c->launches++;
+          return;
+        }
       }
       using Smem = MgSmem<MODE, OUT, RUPD>;
       const int bit = RUPD ? (1 << 30) : (1 << (MODE * 4 + OUT * 2 + DOT));
@@ -1151,6 +1182,8 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if (const char* e = getenv("SPL_NO_RING")) c->no_ring = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_WS")) c->no_ws = atoi(e) != 0;
   if (const char* e = getenv("SPL_TMA")) c->use_tma = atoi(e) != 0;
+  if (const char* e = getenv("SPL_MG_TMA")) c->mg_no_tma = atoi(e) == 0;
+  c->tmaps.reserve(256);
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
 
