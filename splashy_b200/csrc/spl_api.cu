@@ -176,6 +176,7 @@ struct spl_ctx {
   bool use_tma = true;
   std::vector<std::pair<const void*, CUtensorMap>> tmaps;
   std::vector<int> tmap_kind;
+  int tma_l2 = 3;              // CUtensorMapL2promotion of the tensor maps (SPL_TMA_L2: 0 none, 1 64B, 2 128B, 3 256B: 0.3821 vs 0.3848 ms)
   bool mg_no_tma = false;      // SPL_MG_TMA=0: multigrid passes with per-thread cp.async (k_mg_march)
   int mgt_attr_set = 0;
   bool no_ws = false;          // SPL_NO_WS=1: ring kernel without the halo warp (k_phaseA_ring)
@@ -379,7 +380,7 @@ const CUtensorMap* tensor_map_for(spl_ctx* c, const Geo& g, const void* plane0, 
   CUtensorMap m;
   const CUresult r = encode(&m, is_codes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                             3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)c->tma_l2,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return nullptr;
   c->tmaps.emplace_back(plane0, m);
@@ -1183,6 +1184,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if (const char* e = getenv("SPL_NO_WS")) c->no_ws = atoi(e) != 0;
   if (const char* e = getenv("SPL_TMA")) c->use_tma = atoi(e) != 0;
   if (const char* e = getenv("SPL_MG_TMA")) c->mg_no_tma = atoi(e) == 0;
+  if (const char* e = getenv("SPL_TMA_L2")) c->tma_l2 = atoi(e) & 3;
   c->tmaps.reserve(256);
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
