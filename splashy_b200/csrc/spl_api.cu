@@ -1537,6 +1537,9 @@ static int project_impl(spl_ctx* c, double dt, spl_info* info, bool with_advect)
     if (c->d.dtype == SPL_F64)
       LAUNCH(c, k_true_residual<double>, grid_for(c, c->g.ncell), 256, c->g, c->codes,
              reinterpret_cast<const double*>(c->p), reinterpret_cast<double*>(c->r));
+    else if (c->g.nx % 4 == 0 && !c->no_quad)
+      LAUNCH(c, k_true_residual4, grid_for(c, c->g.ncell / 4), 256, c->g, c->codes,
+             reinterpret_cast<const double*>(c->p), reinterpret_cast<float*>(c->r));
     else
       LAUNCH(c, k_true_residual<float>, grid_for(c, c->g.ncell), 256, c->g, c->codes,
              reinterpret_cast<const double*>(c->p), reinterpret_cast<float*>(c->r));

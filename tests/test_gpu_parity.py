@@ -248,7 +248,7 @@ def test_multigrid_fused_residual_update_equals_the_separate_phase_b(monkeypatch
         assert np.array_equal(ga[n], gb[n]), n
 
 
-def test_iterative_refinement_restores_the_divergence_free_residual_in_fp32():
+def test_iterative_refinement_restores_the_divergence_free_residual_in_fp32(monkeypatch):
     """A multigrid solve takes a few large fp32 steps, so its recursive residual drifts from
     b - A x by ~eps32 |A| |x|; one restart from the fp64 true residual (default for fp32 +
     SPL_PC_MG) brings max|div| after the projection down to the level of the many-small-steps
@@ -261,6 +261,14 @@ def test_iterative_refinement_restores_the_divergence_free_residual_in_fp32():
             s.set_refinement(rounds)
             s.upload(lab, U, V, W)
             res[name] = s.project(sc["dt"])
+    monkeypatch.setenv("SPL_NO_QUAD", "1")             # one-cell k_true_residual / div / grad / check
+    with solver_for(sc, dtype=np.float32, tol=1e-6, precond="mg") as s:
+        s.set_refinement(1)
+        s.upload(lab, U, V, W)
+        scalar = s.project(sc["dt"])
+    monkeypatch.delenv("SPL_NO_QUAD")
+    assert scalar["iters"] == res["mg1"]["iters"] and scalar["r_inf"] == res["mg1"]["r_inf"]
+    assert scalar["max_abs_div"] == res["mg1"]["max_abs_div"]
     print({k: (v["iters"], v["max_abs_div"]) for k, v in res.items()})
     assert all(v["converged"] == 1 for v in res.values())
     assert res["mg1"]["max_abs_div"] < 0.5 * res["mg0"]["max_abs_div"]
