@@ -133,6 +133,18 @@ int  spl_upload(spl_ctx* ctx, const uint8_t* media, const void* u,
  * Pressure.fs:16-32 for the current velocities (0 on non-Fluid cells).      */
 int  spl_download(spl_ctx* ctx, void* u, void* v, void* w, void* p, void* div);
 
+/* Cell-centred scalar fields carried by the flow (north_star: "semi-Lagrangian advection of
+ * the staggered MAC velocity and scalar fields"; SURVEY 8d cfg2 "one scalar phi", +8 B/cell).
+ * The reference's Cell record holds none (Cell.fs:11-16), so there is no function to replace:
+ * a scalar takes the same RK2 backtrace as a velocity face (Convection.fs:50-57), started at the
+ * cell centre, and a trilinear sample of itself at the departure point (Convection.fs:21-39;
+ * absent corner = 0); like the velocity, only Fluid cells are updated.  fields = n host
+ * arrays of the box (context dtype; a NULL entry = zeros), n <= SPL_MAX_SCALARS; every later
+ * spl_advect / spl_step / spl_advance advects them with the velocity of the step.          */
+#define SPL_MAX_SCALARS 8
+int  spl_set_scalars(spl_ctx* ctx, int n, const void* const* fields);
+int  spl_get_scalars(spl_ctx* ctx, int n, void* const* fields);
+
 /* ---- the hot path -------------------------------------------------------- */
 /* Convection.apply + Grid.update_velocities (Convection.fs:60-66,
  * Simulator.fs:82)                                                           */
@@ -209,7 +221,7 @@ int  spl_timer_stop(spl_ctx* ctx, float* ms);
 /* per-kernel timing of the PCG iteration: builds the RHS for dt, then runs
  * `iters` (<= 256) iterations with CUDA events around every phase-A, phase-B
  * and x-flush launch; returns the average duration of each in milliseconds
- * (the x flush runs once every SPL_NSBUF = 4 iterations).  The velocity field
+ * (the x flush runs once every SPL_NSBUF = 16 iterations).  The velocity field
  * is not modified (no gradient subtraction).                                   */
 int  spl_profile_pcg(spl_ctx* ctx, double dt, int iters, float* ms_phase_a,
                      float* ms_phase_b, float* ms_xflush);

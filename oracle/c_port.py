@@ -34,6 +34,7 @@ def load():
                                                    C.POINTER(C.c_double)]
     lib.orc_grad_sub.argtypes = [C.c_int] * 3 + [_u8p, _f32p, _f32p, _f32p, _f32p, C.c_float]
     lib.orc_advect.argtypes = [C.c_int] * 3 + [_u8p] + [_f32p] * 6 + [C.c_float]
+    lib.orc_advect_scalar.argtypes = [C.c_int] * 3 + [_u8p] + [_f32p] * 5 + [C.c_float]
     lib.orc_max_div.restype = C.c_double
     lib.orc_max_div.argtypes = [C.c_int] * 3 + [_u8p, _f32p, _f32p, _f32p]
     lib.orc_step.restype = C.c_int
@@ -64,6 +65,14 @@ def advect(labels, U, V, W, dt, h):
     out = [np.empty_like(U) for _ in range(3)]
     lib.orc_advect(nx, ny, nz, labels, U, V, W, *out, float(dt / h))
     return tuple(out)
+
+
+def advect_scalar(labels, U, V, W, S, dt, h):
+    lib = load()
+    nz, ny, nx = labels.shape
+    out = np.empty_like(S)
+    lib.orc_advect_scalar(nx, ny, nz, labels, U, V, W, S, out, float(dt / h))
+    return out
 
 
 def step(labels, U, V, W, dt, h, rho, tol=1e-6, max_iters=20000, fixed_iters=0):

@@ -246,6 +246,33 @@ void orc_advect(int nx, int ny, int nz, const uint8_t* lab, const float* u, cons
       }
 }
 
+/* cell-centred scalar carried by the flow: the trace of Convection.fs:50-57 from the cell
+ * centre, trilinear sample of the scalar (Convection.fs:21-39); dense_ref.advect_scalar */
+void orc_advect_scalar(int nx, int ny, int nz, const uint8_t* lab, const float* u,
+                       const float* v, const float* w, const float* s, float* s2,
+                       float dt_over_h) {
+  box_t b = {nx, ny, nz, (int64_t)nx * ny, (int64_t)nx * ny * nz};
+  const float c = -dt_over_h, h = 0.5f;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i) {
+        const int64_t idx = (int64_t)k * b.plane + (int64_t)j * nx + i;
+        float val = s[idx];
+        if (lab[idx] == FLUID) {
+          const float u0 = samplef(u, &b, i, j, k, -h, 0.f, 0.f);
+          const float v0 = samplef(v, &b, i, j, k, 0.f, -h, 0.f);
+          const float w0 = samplef(w, &b, i, j, k, 0.f, 0.f, -h);
+          const float mx = h * c * u0, my = h * c * v0, mz = h * c * w0;
+          const float u1 = samplef(u, &b, i, j, k, mx - h, my, mz);
+          const float v1 = samplef(v, &b, i, j, k, mx, my - h, mz);
+          const float w1 = samplef(w, &b, i, j, k, mx, my, mz - h);
+          val = samplef(s, &b, i, j, k, c * u1, c * v1, c * w1);
+        }
+        s2[idx] = val;
+      }
+}
+
 /* Pressure.fs:145-149: max |divergence| over Fluid */
 double orc_max_div(int nx, int ny, int nz, const uint8_t* codes, const float* u,
                    const float* v, const float* w) {

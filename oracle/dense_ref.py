@@ -479,6 +479,31 @@ def advect(labels, U, V, W, dt: float, h: float, forward: bool = False):
     return tuple(out)
 
 
+def advect_scalar(labels, U, V, W, S, dt: float, h: float, forward: bool = False):
+    """A cell-centred scalar carried by the flow: the RK2-midpoint backtrace of
+    Convection.fs:50-57 started at the cell centre (i, j, k) instead of a face centre,
+    then a trilinear sample of the scalar itself at the departure point with the weights
+    of Convection.fs:21-39 (a corner outside the box contributes 0).  The reference's Cell
+    has no scalar (Cell.fs:11-16); this defines north_star's "velocity and scalar fields"
+    in the same intended semantics as ``advect``.  Only Fluid cells are updated; reads the
+    OLD velocity field (Jacobi, like ``advect``)."""
+    nz, ny, nx = S.shape
+    t = S.dtype.type
+    kk, jj, ii = np.meshgrid(np.arange(nz, dtype=S.dtype),
+                             np.arange(ny, dtype=S.dtype),
+                             np.arange(nx, dtype=S.dtype), indexing="ij")
+    sgn = t(1.0) if forward else t(-1.0)
+    c = t(dt / h)
+    hlf = t(0.5)
+    u0, v0, w0 = velocity_at(U, V, W, ii, jj, kk)
+    mx = ii + sgn * hlf * c * u0
+    my = jj + sgn * hlf * c * v0
+    mz = kk + sgn * hlf * c * w0
+    u1, v1, w1 = velocity_at(U, V, W, mx, my, mz)
+    new = sample(S, ii + sgn * c * u1, jj + sgn * c * v1, kk + sgn * c * w1)
+    return np.where(labels == FLUID, new, S).astype(S.dtype)
+
+
 def add_forces(labels, U, V, W, dt: float, gravity=(0.0, -9.81, 0.0)):
     """Forces.fs:6-12: v += g dt on Fluid cells."""
     fl = labels == FLUID

@@ -79,6 +79,8 @@ SYMBOLS = {
     "spl_nccl_unique_id": (C.c_int, [_VP]),
     "spl_upload": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "spl_download": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "spl_set_scalars": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
+    "spl_get_scalars": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
     "spl_advect": (C.c_int, [_VP, C.c_double, C.POINTER(SplInfo)]),
     "spl_add_forces": (C.c_int, [_VP, C.c_double]),
     "spl_add_viscosity": (C.c_int, [_VP, C.c_double]),

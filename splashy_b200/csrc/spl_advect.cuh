@@ -229,18 +229,39 @@ __device__ __forceinline__ T advect_face(const FieldView<T>& U, const FieldView<
   return sample(F, i, j, k, dx, dy, dz, esc);
 }
 
+// cell-centred scalar: the same RK2 trace from the cell centre (i, j, k), then a trilinear
+// sample of the scalar itself at the departure point (corners outside the box contribute 0,
+// like the velocity components: Convection.fs:36-38).  The reference's Cell carries no scalar
+// (Cell.fs:11-16); this is north_star's "velocity and scalar fields" (SURVEY 8d cfg2 "+8 B").
+template <typename T>
+__device__ __forceinline__ T advect_centre(const FieldView<T>& U, const FieldView<T>& V,
+                                           const FieldView<T>& W, const FieldView<T>& S, int i,
+                                           int j, int k, T c /* sgn*dt/h */, unsigned& esc) {
+  const T h = T(0.5), o = T(0);
+  const T u0 = sample(U, i, j, k, -h, o, o, esc);
+  const T v0 = sample(V, i, j, k, o, -h, o, esc);
+  const T w0 = sample(W, i, j, k, o, o, -h, esc);
+  const T mx = h * c * u0, my = h * c * v0, mz = h * c * w0;
+  const T u1 = sample(U, i, j, k, mx - h, my, mz, esc);
+  const T v1 = sample(V, i, j, k, mx, my - h, mz, esc);
+  const T w1 = sample(W, i, j, k, mx, my, mz - h, esc);
+  return sample(S, i, j, k, c * u1, c * v1, c * w1, esc);
+}
+
 // second pass: the cells the hot kernel listed (box shell, slab ends, large
-// displacements), one thread per listed cell.
+// displacements), one thread per listed cell.  s / s2 (nullable): a scalar field advected
+// with the same velocity; do_vel = 0 leaves u2, v2, w2 alone (scalar-only pass).
 template <typename T>
 __global__ void __launch_bounds__(256, 2)
 k_advect_rest(Geo g, const T* __restrict__ u, const T* __restrict__ v,
               const T* __restrict__ w, T* __restrict__ u2, T* __restrict__ v2,
-              T* __restrict__ w2, T c, const int* __restrict__ worklist,
-              Scal* __restrict__ sc) {
+              T* __restrict__ w2, const T* __restrict__ s, T* __restrict__ s2, int do_vel, T c,
+              const int* __restrict__ worklist, Scal* __restrict__ sc) {
   FieldView<T> U{u, g.nx, g.ny, -g.z0, g.nzg - g.z0, -g.hz, g.nz + g.hz, g.plane};
-  FieldView<T> V = U, W = U;
+  FieldView<T> V = U, W = U, S = U;
   V.f = v;
   W.f = w;
+  S.f = s;
   unsigned esc = 0;
   const unsigned n = sc->wl_count;
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
@@ -249,9 +270,37 @@ k_advect_rest(Geo g, const T* __restrict__ u, const T* __restrict__ v,
     const int r = idx / g.nx;
     const int j = r % g.ny;
     const int k = r / g.ny;
-    u2[idx] = advect_face<T>(U, V, W, 0, i, j, k, c, esc);
-    v2[idx] = advect_face<T>(U, V, W, 1, i, j, k, c, esc);
-    w2[idx] = advect_face<T>(U, V, W, 2, i, j, k, c, esc);
+    if (do_vel) {
+      u2[idx] = advect_face<T>(U, V, W, 0, i, j, k, c, esc);
+      v2[idx] = advect_face<T>(U, V, W, 1, i, j, k, c, esc);
+      w2[idx] = advect_face<T>(U, V, W, 2, i, j, k, c, esc);
+    }
+    if (s) s2[idx] = advect_centre<T>(U, V, W, S, i, j, k, c, esc);
+  }
+  if (esc) atomicAdd(&sc->escapes, 1ull);
+}
+
+// generic scalar pass (fp64, ragged nx, quirk contexts): every corner bounds-tested
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+k_advect_scalar(Geo g, const uint8_t* __restrict__ media, const T* __restrict__ u,
+                const T* __restrict__ v, const T* __restrict__ w, const T* __restrict__ s,
+                T* __restrict__ s2, T c, Scal* __restrict__ sc) {
+  FieldView<T> U{u, g.nx, g.ny, -g.z0, g.nzg - g.z0, -g.hz, g.nz + g.hz, g.plane};
+  FieldView<T> V = U, W = U, S = U;
+  V.f = v;
+  W.f = w;
+  S.f = s;
+  unsigned esc = 0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < g.ncell;
+       idx += (long long)gridDim.x * blockDim.x) {
+    T val = s[idx];
+    if (media[idx] == FLUID) {
+      const int i = (int)(idx % g.nx);
+      const long long t = idx / g.nx;
+      val = advect_centre<T>(U, V, W, S, i, (int)(t % g.ny), (int)(t / g.ny), c, esc);
+    }
+    s2[idx] = val;
   }
   if (esc) atomicAdd(&sc->escapes, 1ull);
 }

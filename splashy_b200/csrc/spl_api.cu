@@ -24,6 +24,7 @@
 
 #include "../../include/splashy_cuda.h"
 #include "spl_advect.cuh"
+#include "spl_advect_tma.cuh"
 #include "spl_common.cuh"
 #include "spl_mg.cuh"
 #include "spl_pcg.cuh"
@@ -181,6 +182,15 @@ struct spl_ctx {
   int mgt_attr_set = 0;
   bool no_ws = false;          // SPL_NO_WS=1: ring kernel without the halo warp (k_phaseA_ring)
   bool no_quad = false;        // SPL_NO_QUAD=1: one-cell-per-thread div / grad / check kernels
+  // cell-centred scalar fields advected with the velocity (spl_set_scalars); scal2 = target
+  std::vector<char*> scal;
+  char* scal2 = nullptr;
+  // tile-staged advection (spl_advect_tma.cuh; default for fp32, nx % 4 = 0; SPL_ADV_TMA=0: the
+  // L1-gather kernel k_advect)
+  bool adv_tma = true;
+  bool adv_fuse = true;        // SPL_ADV_FUSE=0: the first scalar gets its own pass
+  int adv_zchunk = 0;          // SPL_ADV_ZCHUNK: planes per CTA (0 = automatic)
+  int adv_attr_set = 0;
   int64_t launches = 0;
   double rhs_dt = 0.0;
   std::string err;
@@ -353,7 +363,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-enum { TM_F = 0, TM_C = 1, TM_E = 2 };   // fp32 raw tile, u8 code tile, coarse-correction tile
+// fp32 raw tile, u8 code tile, coarse-correction tile, advection raw tiles (8 / 16 row warps)
+enum { TM_F = 0, TM_C = 1, TM_E = 2, TM_A8 = 3, TM_A16 = 4 };
 
 const CUtensorMap* tensor_map_for(spl_ctx* c, const Geo& g, const void* plane0, int kind) {
   for (auto& kv : c->tmaps)
@@ -376,6 +387,8 @@ const CUtensorMap* tensor_map_for(spl_ctx* c, const Geo& g, const void* plane0, 
   cuuint32_t box[3] = {(cuuint32_t)TMA_BX, (cuuint32_t)TMA_BY, 1u};
   if (kind == TM_C) box[0] = TMA_CX;
   if (kind == TM_E) { box[0] = MGT_EX; box[1] = MGT_EY; }
+  if (kind == TM_A8) { box[0] = ADVT_ROW; box[1] = AdvT<8>::ROWS; }
+  if (kind == TM_A16) { box[0] = ADVT_ROW; box[1] = AdvT<16>::ROWS; }
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   CUtensorMap m;
   const CUresult r = encode(&m, is_codes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
@@ -393,27 +406,102 @@ template <typename T>
 struct Impl {
   static T* P(char* p) { return reinterpret_cast<T*>(p); }
 
+  // tile-staged advection (spl_advect_tma.cuh): one launch of k_advect_tma<NW, VEL, NSC>
+  // followed by the worklist pass.  s_in / s_out: the scalar of an NSC = 1 pass.
+  template <int NW, int VEL, int NSC>
+  static bool advect_tma_pass(spl_ctx* c, float cc, const char* s_in, char* s_out) {
+    if constexpr (std::is_same<T, float>::value) {
+      const Geo& g = c->g;
+      const int kind = NW == 8 ? TM_A8 : TM_A16;
+      const CUtensorMap* mu = tensor_map_for(c, g, c->u, kind);
+      const CUtensorMap* mv = tensor_map_for(c, g, c->v, kind);
+      const CUtensorMap* mw = tensor_map_for(c, g, c->w, kind);
+      const CUtensorMap* ms = NSC ? tensor_map_for(c, g, s_in, kind) : mu;
+      if (!mu || !mv || !mw || !ms) return false;
+      using Smem = AdvTSmem<NW, 3 + NSC>;
+      const int bit = 1 << ((NW == 16 ? 4 : 0) + VEL * 2 + NSC);
+      if (!(c->adv_attr_set & bit)) {
+        if (cudaFuncSetAttribute(k_advect_tma<NW, VEL, NSC>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(Smem)) != cudaSuccess)
+          return false;
+        c->adv_attr_set |= bit;
+      }
+      const int tx = (g.nx + 31) / 32, ty = (g.ny + 2 * NW - 1) / (2 * NW);
+      // planes per CTA: ~8 waves of CTAs, at least 32 planes (6 extra planes are staged per chunk)
+      int zc = c->adv_zchunk;
+      if (zc <= 0) {
+        const int slots = c->sms * ((NW <= 8 && NSC == 0) ? 2 : 1);
+        int gz = (8 * slots + tx * ty - 1) / (tx * ty);
+        if (gz < 1) gz = 1;
+        zc = (g.nz + gz - 1) / gz;
+        if (zc < 32) zc = 32;
+      }
+      if (zc > g.nz) zc = g.nz;
+      int gz = (g.nz + zc - 1) / zc;
+      while (gz > 65535) { zc *= 2; gz = (g.nz + zc - 1) / zc; }
+      int* worklist = reinterpret_cast<int*>(c->q);
+      cudaMemsetAsync(&c->sc->wl_count, 0, sizeof(unsigned), c->stream);
+      k_advect_tma<NW, VEL, NSC><<<dim3(tx, ty, gz), dim3(32, NW + 1), sizeof(Smem), c->stream>>>(
+          *mu, *mv, *mw, *ms, g, c->media, P(c->u2), P(c->v2), P(c->w2), P(s_out), cc, worklist,
+          c->sc, zc);
+      c->launches++;
+      LAUNCH(c, k_advect_rest<T>, grid_for(c, g.ncell) < 592 ? grid_for(c, g.ncell) : 592, 256, g,
+             P(c->u), P(c->v), P(c->w), P(c->u2), P(c->v2), P(c->w2),
+             NSC ? reinterpret_cast<const T*>(s_in) : nullptr, P(s_out), VEL, cc, worklist, c->sc);
+      return true;
+    }
+    return false;
+  }
+
   static int advect(spl_ctx* c, double dt) {
     const Geo& g = c->g;
     int rc = exchange_velocity(c, g.hz);
     if (rc) return rc;
+    for (char* s : c->scal)
+      if ((rc = exchange_halo(c, s, c->esz, nccl_real(c), g.hz))) return rc;
     const int grid = grid_for(c, g.ncell);
+    const T cc = T(-(dt / c->d.h));
+    size_t first_scalar = 0;
     if (c->d.quirks) {
       QuirkCfg q{c->d.quirks, c->d.origin[0], c->d.origin[1], c->d.origin[2] + g.z0, c->d.h};
       CU(cudaMemsetAsync(c->flag, 0, sizeof(int), c->stream));
       LAUNCH(c, k_advect_quirk<T>, grid, 256, g, q, c->media, P(c->u), P(c->v), P(c->w),
              P(c->u2), P(c->v2), P(c->w2), dt, c->sc, c->flag);
     } else {
-      const T cc = T(-(dt / c->d.h));
-      const dim3 agrid((g.nx + 31) / 32, (g.ny + 7) / 8, g.nz < 65535 ? g.nz : 65535);
-      // cells the hot kernel cannot prove safe go to a worklist kept in the PCG
-      // scratch field q (>= 4 B per cell, free during advection)
-      int* worklist = reinterpret_cast<int*>(c->q);
-      CU(cudaMemsetAsync(&c->sc->wl_count, 0, sizeof(unsigned), c->stream));
-      LAUNCH(c, k_advect<T>, agrid, dim3(32, 8), g, c->media, P(c->u), P(c->v), P(c->w),
-             P(c->u2), P(c->v2), P(c->w2), cc, worklist, c->sc);
-      LAUNCH(c, k_advect_rest<T>, grid, 256, g, P(c->u), P(c->v), P(c->w), P(c->u2),
-             P(c->v2), P(c->w2), cc, worklist, c->sc);
+      bool done = false;
+      if constexpr (std::is_same<T, float>::value) {
+        if (c->adv_tma && c->use_tma && g.nx % 4 == 0) {
+          if (!c->scal.empty() && c->adv_fuse) {      // velocity + the first scalar in one pass
+            done = advect_tma_pass<16, 1, 1>(c, cc, c->scal[0], c->scal2);
+            if (done) { std::swap(c->scal[0], c->scal2); first_scalar = 1; }
+          }
+          if (!done) done = advect_tma_pass<8, 1, 0>(c, cc, nullptr, nullptr);
+          if (done)
+            for (size_t i = first_scalar; i < c->scal.size(); ++i) {
+              if (!advect_tma_pass<16, 0, 1>(c, cc, c->scal[i], c->scal2)) break;
+              std::swap(c->scal[i], c->scal2);
+              first_scalar = i + 1;
+            }
+        }
+      }
+      if (!done) {
+        const dim3 agrid((g.nx + 31) / 32, (g.ny + 7) / 8, g.nz < 65535 ? g.nz : 65535);
+        // cells the hot kernel cannot prove safe go to a worklist kept in the PCG
+        // scratch field q (>= 4 B per cell, free during advection)
+        int* worklist = reinterpret_cast<int*>(c->q);
+        CU(cudaMemsetAsync(&c->sc->wl_count, 0, sizeof(unsigned), c->stream));
+        LAUNCH(c, k_advect<T>, agrid, dim3(32, 8), g, c->media, P(c->u), P(c->v), P(c->w),
+               P(c->u2), P(c->v2), P(c->w2), cc, worklist, c->sc);
+        LAUNCH(c, k_advect_rest<T>, grid, 256, g, P(c->u), P(c->v), P(c->w), P(c->u2),
+               P(c->v2), P(c->w2), (const T*)nullptr, (T*)nullptr, 1, cc, worklist, c->sc);
+      }
+    }
+    // scalars not covered above: generic bounds-tested pass, traced through the OLD velocity
+    for (size_t i = first_scalar; i < c->scal.size(); ++i) {
+      LAUNCH(c, k_advect_scalar<T>, grid, 256, g, c->media, P(c->u), P(c->v), P(c->w),
+             P(c->scal[i]), P(c->scal2), cc, c->sc);
+      std::swap(c->scal[i], c->scal2);
     }
     CU(cudaGetLastError());
     std::swap(c->u, c->u2);
@@ -1188,6 +1276,9 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   c->tmaps.reserve(256);
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
+  if (const char* e = getenv("SPL_ADV_TMA")) c->adv_tma = atoi(e) != 0;
+  if (const char* e = getenv("SPL_ADV_FUSE")) c->adv_fuse = atoi(e) != 0;
+  if (const char* e = getenv("SPL_ADV_ZCHUNK")) c->adv_zchunk = atoi(e);
 
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
@@ -1438,6 +1529,40 @@ int spl_advect(spl_ctx* c, double dt, spl_info* info) {
   }
   if ((c->d.quirks && *c->hflag) || c->hsc->escapes)
     return fail(c, SPL_E_TRACE, "Backwards particle trace went too far.");   // Convection.fs:65
+  return SPL_OK;
+}
+
+int spl_set_scalars(spl_ctx* c, int n, const void* const* fields) {
+  if (!c || n < 0 || n > SPL_MAX_SCALARS || (n > 0 && !fields)) return SPL_E_BADARG;
+  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_set_scalars before spl_upload");
+  CU(cudaSetDevice(c->d.device));
+  int rc;
+  while ((int)c->scal.size() < n) {
+    char* p0 = nullptr;
+    if ((rc = alloc_field(c, 48 + (int)c->scal.size(), c->esz, &p0, 0))) return rc;
+    c->scal.push_back(p0);
+  }
+  if (n > 0 && !c->scal2 && (rc = alloc_field(c, 48 + SPL_MAX_SCALARS, c->esz, &c->scal2, 0)))
+    return rc;
+  c->scal.resize(n);        // dropped fields keep their allocation until spl_destroy
+  const size_t nb = (size_t)c->g.ncell * c->esz;
+  for (int i = 0; i < n; ++i) {
+    if (fields[i]) CU(cudaMemcpyAsync(c->scal[i], fields[i], nb, cudaMemcpyHostToDevice, c->stream));
+    else CU(cudaMemsetAsync(c->scal[i], 0, nb, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return SPL_OK;
+}
+
+int spl_get_scalars(spl_ctx* c, int n, void* const* fields) {
+  if (!c || n < 0 || (n > 0 && !fields)) return SPL_E_BADARG;
+  if (n > (int)c->scal.size())
+    return fail(c, SPL_E_BADARG, "spl_get_scalars: %d requested, %d set", n, (int)c->scal.size());
+  CU(cudaSetDevice(c->d.device));
+  const size_t nb = (size_t)c->g.ncell * c->esz;
+  for (int i = 0; i < n; ++i)
+    if (fields[i]) CU(cudaMemcpyAsync(fields[i], c->scal[i], nb, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return SPL_OK;
 }
 

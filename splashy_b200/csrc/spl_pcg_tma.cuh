@@ -48,10 +48,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
                "r"(bytes)
                : "memory");
 }
-// bounded spin: a wrong byte count or descriptor must abort the launch, not hang the GPU
+// bounded spin: a wrong byte count or descriptor must abort the launch, not hang the GPU.
+// try_wait itself may suspend the thread for a system-dependent time, so the bound is wall
+// time (4 s on %globaltimer, sampled every 256 failed polls), not a poll count.
 __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity) {
   const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  for (unsigned spin = 0;; ++spin) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 1;; ++spin) {
     unsigned ok;
     asm volatile(
         "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
@@ -60,7 +63,12 @@ __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsig
         : "r"(a), "r"(parity)
         : "memory");
     if (ok) return;
-    if (spin > (1u << 24)) __trap();
+    if ((spin & 255u) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,

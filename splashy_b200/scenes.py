@@ -139,6 +139,20 @@ def random_box(nx: int, ny: int, nz: int, *, seed: int = 0, dtype=np.float64,
                 name=f"random_{nx}x{ny}x{nz}_s{seed}")
 
 
+def blob(nx: int, ny: int, nz: int, *, z0: int = 0, nz_global: Optional[int] = None,
+         dtype=np.float32) -> np.ndarray:
+    """cfg2's "one scalar phi = Gaussian blob" (SURVEY 8d): centred at (0.5, 0.6, 0.5) of
+    the global box, sigma = 1/8 of the smallest extent > 1; values in (0, 1]."""
+    nzg = nz_global or nz
+    ext = [e for e in (nx, ny, nzg) if e > 1]
+    sig = max(1.0, min(ext) / 8.0)
+    x = np.arange(nx, dtype=np.float64) - 0.5 * (nx - 1)
+    y = np.arange(ny, dtype=np.float64) - 0.6 * (ny - 1)
+    z = np.arange(z0, z0 + nz, dtype=np.float64) - 0.5 * (nzg - 1)
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij", sparse=True)
+    return np.exp(-(X * X + Y * Y + Z * Z) / (2.0 * sig * sig)).astype(dtype)
+
+
 def slab_of(scene: Dict, z0: int, nz: int) -> Dict:
     """Planes [z0, z0 + nz) of a whole-box scene."""
     out = dict(scene)

@@ -162,6 +162,22 @@ class Solver:
             ptr("div") if div else None))
         return res
 
+    def set_scalars(self, fields: Sequence[np.ndarray]) -> None:
+        """Cell-centred scalar fields advected with the velocity by every later advect / step."""
+        arrs = [np.ascontiguousarray(f, dtype=self.dtype) for f in fields]
+        for a in arrs:
+            if a.shape != self.shape:
+                raise ValueError(f"expected shape {self.shape}, got {a.shape}")
+        ptrs = (C.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
+        self._nscal = len(arrs)
+        self._check(self._lib.spl_set_scalars(self._ctx, len(arrs), ptrs))
+
+    def get_scalars(self):
+        outs = [np.empty(self.shape, dtype=self.dtype) for _ in range(self._nscal)]
+        ptrs = (C.c_void_p * max(len(outs), 1))(*[a.ctypes.data for a in outs])
+        self._check(self._lib.spl_get_scalars(self._ctx, len(outs), ptrs))
+        return outs
+
     # -- the hot path --------------------------------------------------------------
     def _call(self, fn, *args) -> Dict:
         info = nat.SplInfo()

@@ -412,6 +412,127 @@ def test_advect_fp32_within_1e5_relative(name):
         assert np.abs(got[n] - r).max() <= 1e-5 * vs, n   # north_star tolerance
 
 
+# ---- scalar fields (north_star "velocity and scalar fields") ---------------------------------
+SCALAR_SCENES = {
+    "vortex_ragged": lambda dt: scenes.vortex(23, 17, 9, dtype=dt),
+    "vortex_vec": lambda dt: scenes.vortex(40, 24, 16, dtype=dt),
+    "vortex_tiles": lambda dt: scenes.vortex(72, 40, 21, dtype=dt),      # several tiles, ragged tile edges
+    "smoke2d": lambda dt: scenes.smoke2d(80, dtype=dt),
+    "random": lambda dt: scenes.random_box(24, 14, 10, seed=9, vel=15.0, dtype=dt, dt=1.0),
+}
+
+
+def scalar_fields(sc, dtype, n=1):
+    nz, ny, nx = sc["labels"].shape
+    rng = np.random.default_rng(11)
+    out = [scenes.blob(nx, ny, nz, dtype=dtype)]
+    for _ in range(n - 1):
+        out.append(rng.uniform(-1.0, 1.0, sc["labels"].shape).astype(dtype))
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(SCALAR_SCENES))
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_scalar_advection_matches_oracle(name, dtype):
+    """fp64: 1e-12; fp32: the north_star bar for advected fields, 1e-5 relative.  Three scalars:
+    the first rides on the velocity pass, the others take scalar-only passes; the velocity
+    result must not depend on scalars being present."""
+    sc = SCALAR_SCENES[name](dtype)
+    lab, U, V, W = fields(sc, dtype)
+    S = scalar_fields(sc, dtype, 3)
+    with solver_for(sc, dtype=dtype) as s:
+        s.upload(lab, U, V, W)
+        s.set_scalars(S)
+        s.advect(sc["dt"])
+        got = s.download()
+        gs = s.get_scalars()
+    with solver_for(sc, dtype=dtype) as s:
+        s.upload(lab, U, V, W)
+        s.advect(sc["dt"])
+        plain = s.download()
+    f64 = [a.astype(np.float64) for a in (U, V, W)]
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    for k, Sk in enumerate(S):
+        ref = dr.advect_scalar(lab, *f64, Sk.astype(np.float64), sc["dt"], sc["h"])
+        assert np.abs(gs[k] - ref).max() <= tol * vscale(Sk), (name, k)
+    vs = vscale(U, V, W)
+    refv = dr.advect(lab, *f64, sc["dt"], sc["h"])
+    for n, r in zip("UVW", refv):
+        assert np.abs(got[n] - r).max() <= tol * vs, n
+        assert np.abs(got[n] - plain[n]).max() <= (0 if dtype == np.float64 else 2e-6 * vs), n
+
+
+def test_scalar_advection_exact_shift_on_the_gpu():
+    """Uniform flow of (2, -1, 1) cells per step: every departure point is a cell centre, the
+    interior of the new field is the old field shifted -- exact in fp32 as well."""
+    nz, ny, nx = 20, 36, 40
+    rng = np.random.default_rng(5)
+    lab = np.full((nz, ny, nx), dr.FLUID, dtype=np.uint8)
+    h, dt = 10.0, 1.0
+    U = np.full(lab.shape, 2.0 * h / dt, dtype=np.float32)
+    V = np.full(lab.shape, -1.0 * h / dt, dtype=np.float32)
+    W = np.full(lab.shape, 1.0 * h / dt, dtype=np.float32)
+    S = rng.uniform(0.0, 1.0, lab.shape).astype(np.float32)
+    with Solver(nx, ny, nz, dtype=np.float32, h=h) as s:
+        s.upload(lab, U, V, W)
+        s.set_scalars([S])
+        s.advect(dt)
+        got = s.get_scalars()[0]
+    want = np.zeros_like(S)
+    want[1:, :-1, 2:] = S[:-1, 1:, :-2]
+    inner = (slice(3, -3), slice(3, -3), slice(4, -4))
+    assert np.array_equal(got[inner], want[inner])
+
+
+def test_tile_staged_advection_equals_the_gather_kernel(monkeypatch):
+    """k_advect_tma (shared-memory ring, packed pairs) against k_advect (L1 gathers): same
+    samples, the lerps associate differently -> a few ulp."""
+    sc = scenes.vortex(96, 40, 37, dtype=np.float32)
+    lab, U, V, W = fields(sc, np.float32)
+    S = scalar_fields(sc, np.float32, 2)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SPL_ADV_TMA", mode)
+        with solver_for(sc, dtype=np.float32) as s:
+            s.upload(lab, U, V, W)
+            s.set_scalars(S)
+            s.advect(sc["dt"])
+            res[mode] = (s.download(), s.get_scalars())
+    vs = vscale(U, V, W)
+    for n in "UVW":
+        assert np.abs(res["1"][0][n] - res["0"][0][n]).max() <= 2e-6 * vs, n
+    for a, b in zip(res["1"][1], res["0"][1]):
+        assert np.abs(a - b).max() <= 2e-6
+    # the two paths really are different kernels: the lerps round differently somewhere
+    assert any(not np.array_equal(res["1"][0][n], res["0"][0][n]) for n in "UVW")
+
+
+def test_scalars_ride_through_step_and_nan_velocities_do_not_fault():
+    """spl_step advects the scalars too; a NaN velocity must surface as an error code, not as
+    a shared-memory fault of the tile-staged kernel."""
+    sc = scenes.vortex(40, 24, 16, dtype=np.float32)
+    lab, U, V, W = fields(sc, np.float32)
+    S = scalar_fields(sc, np.float32, 1)
+    with solver_for(sc, dtype=np.float32, tol=1e-6) as s:
+        s.upload(lab, U, V, W)
+        s.set_scalars(S)
+        s.step(sc["dt"])
+        gs = s.get_scalars()[0]
+    ref = dr.advect_scalar(lab, *(a.astype(np.float64) for a in (U, V, W)),
+                           S[0].astype(np.float64), sc["dt"], sc["h"])
+    assert np.abs(gs - ref).max() <= 1e-5
+    U2 = U.copy()
+    U2[8, 12, 20] = np.nan
+    U2[9, 12, 21] = np.inf
+    with solver_for(sc, dtype=np.float32) as s:
+        s.upload(lab, U2, V, W)
+        s.set_scalars(S)
+        with pytest.raises(SplashyError):
+            s.step(sc["dt"])
+        s.upload(lab, U, V, W)          # the context is still usable
+        s.advect(sc["dt"])
+
+
 @pytest.mark.parametrize("cfl", [(2.9, -2.9, 2.9), (-2.95, 2.95, -2.95), (2.4, 2.4, -2.4),
                                  (-0.3, 2.97, 0.1)])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

@@ -171,3 +171,50 @@ def test_multigrid_chebyshev_weights():
     assert abs(w[0] - 0.5695) < 1e-3 and abs(w[1] - 1.7321) < 1e-3
     assert dr.mg_weights(1) == [6.0 / 7.0] or abs(dr.mg_weights(1)[0] - 6.0 / 7.0) < 1e-15
     assert dr.mg_weights(3, omega=2.0 / 3.0) == [2.0 / 3.0] * 3
+
+
+# --------------------------------------------------------------------------
+# scalar advection (north_star "velocity and scalar fields"; no reference counterpart)
+# --------------------------------------------------------------------------
+def test_scalar_advection_shifts_exactly_under_a_uniform_integer_flow():
+    """dt * velocity = (2, -1, 1) cells everywhere: the departure point of every cell is a
+    cell centre, so the new field is the old one shifted (zeros enter from outside)."""
+    nz, ny, nx = 9, 10, 12
+    rng = np.random.default_rng(5)
+    lab = np.full((nz, ny, nx), dr.FLUID, dtype=np.uint8)
+    h, dt = 10.0, 1.0
+    U = np.full(lab.shape, 2.0 * h / dt)
+    V = np.full(lab.shape, -1.0 * h / dt)
+    W = np.full(lab.shape, 1.0 * h / dt)
+    S = rng.uniform(0.0, 1.0, lab.shape)
+    got = dr.advect_scalar(lab, U, V, W, S, dt, h)
+    # interior cells whose whole RK2 footprint sees the uniform flow
+    want = np.zeros_like(S)
+    want[1:, :-1, 2:] = S[:-1, 1:, :-2]
+    inner = (slice(3, -3), slice(3, -3), slice(4, -4))
+    assert np.abs(got[inner] - want[inner]).max() <= 1e-13
+
+
+def test_scalar_advection_keeps_constants_and_non_fluid_cells():
+    sc = scenes.vortex(24, 20, 16, cfl=1.7, dtype=np.float64)
+    lab = sc["labels"]
+    S = np.full(lab.shape, 3.25)
+    got = dr.advect_scalar(lab, sc["U"], sc["V"], sc["W"], S, sc["dt"], sc["h"])
+    inner = (slice(4, -4),) * 3                 # footprint inside the box: weights sum to 1
+    assert np.abs(got[inner] - 3.25).max() <= 1e-12
+    S2 = np.random.default_rng(1).uniform(size=lab.shape)
+    got2 = dr.advect_scalar(lab, sc["U"], sc["V"], sc["W"], S2, sc["dt"], sc["h"])
+    assert np.array_equal(got2[lab != dr.FLUID], S2[lab != dr.FLUID])
+    # bounded by the data (trilinear weights are a convex combination; outside = 0)
+    assert got2.min() >= 0.0 and got2.max() <= S2.max() + 1e-15
+
+
+def test_scalar_advection_c_port_matches_numpy():
+    from oracle import c_port
+    sc = scenes.vortex(40, 24, 16, cfl=2.0)
+    lab = sc["labels"]
+    U, V, W = (np.ascontiguousarray(sc[k], dtype=np.float32) for k in "UVW")
+    S = scenes.blob(40, 24, 16)
+    got = c_port.advect_scalar(lab, U, V, W, S, sc["dt"], sc["h"])
+    ref = dr.advect_scalar(lab, *(a.astype(np.float64) for a in (U, V, W, S)), sc["dt"], sc["h"])
+    assert np.abs(got - ref).max() <= 2e-6
