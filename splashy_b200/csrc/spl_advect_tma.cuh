@@ -117,18 +117,22 @@ __device__ __forceinline__ AdvAx2 adv_split2(pk2 o, pk2 magic) {
 // trilinear samples of one staged field at (cell + offset) for the two cells of a thread.
 // F = ring of the field, tbm = index of the first cell in the raw tile with the magic constants
 // of the x / y terms folded in (second cell: + DB), kcm likewise for the plane -> slot term.
+// The index is clamped (unsigned min) so that a wild offset -- NaN, Inf, or beyond ADV_MAXOFF:
+// cells that are flagged and recomputed by k_advect_rest -- still reads inside the ring; there
+// is no branch on the flags, so the samples of the three faces interleave freely.
 template <int NW>
 __device__ __forceinline__ pk2 adv_tri2(const float* __restrict__ F, unsigned tbm, unsigned kcm,
                                         const AdvAx2& X, const AdvAx2& Y, const AdvAx2& Z) {
   constexpr int PL = AdvT<NW>::PL;
   constexpr int ROW = ADVT_ROW;
+  constexpr unsigned LIMIT = (unsigned)(ADVT_SLOTS * PL - ROW - 2);
   const unsigned xa = (unsigned)X.t, xb = (unsigned)(X.t >> 32);
   const unsigned ya = (unsigned)Y.t, yb = (unsigned)(Y.t >> 32);
   const unsigned za = (unsigned)Z.t, zb = (unsigned)(Z.t >> 32);
   const unsigned sa = (za + kcm) & (ADVT_SLOTS - 1);
   const unsigned sb = (zb + kcm) & (ADVT_SLOTS - 1);
-  const float* __restrict__ pa = F + (sa * PL + (ya * ROW + xa) + tbm);
-  const float* __restrict__ pb = F + (sb * PL + (yb * ROW + xb) + (tbm + AdvT<NW>::DB));
+  const float* __restrict__ pa = F + min(sa * PL + (ya * ROW + xa) + tbm, LIMIT);
+  const float* __restrict__ pb = F + min(sb * PL + (yb * ROW + xb) + (tbm + AdvT<NW>::DB), LIMIT);
   const pk2 c000 = pk(pa[0], pb[0]), c100 = pk(pa[1], pb[1]);
   const pk2 c010 = pk(pa[ROW], pb[ROW]), c110 = pk(pa[ROW + 1], pb[ROW + 1]);
   const pk2 c001 = pk(pa[PL], pb[PL]), c101 = pk(pa[PL + 1], pb[PL + 1]);
@@ -138,16 +142,42 @@ __device__ __forceinline__ pk2 adv_tri2(const float* __restrict__ F, unsigned tb
   return pk_mix(A, B, Z.w);
 }
 
-// largest |offset| of each cell > lim ?  (bit 0: first cell, bit 1: second)
+// some |offset| of a cell > lim ?  (bit 0: first cell, bit 1: second)
 __device__ __forceinline__ unsigned adv_bad2(pk2 a, pk2 b, pk2 c, float lim) {
-  // comparisons, not fmaxf: a NaN offset must count as bad (its bits would index outside the ring)
+  // comparisons, not fmaxf: a NaN offset must count as bad
   const bool oka = (fabsf(pk_lo(a)) <= lim) && (fabsf(pk_lo(b)) <= lim) && (fabsf(pk_lo(c)) <= lim);
   const bool okb = (fabsf(pk_hi(a)) <= lim) && (fabsf(pk_hi(b)) <= lim) && (fabsf(pk_hi(c)) <= lim);
   return (oka ? 0u : 1u) | (okb ? 0u : 2u);
 }
-// zero the offsets of the flagged cells so that their (discarded) samples stay inside the ring
-__device__ __forceinline__ pk2 adv_zero_bad(pk2 v, unsigned bad) {
-  return pk((bad & 1u) ? 0.f : pk_lo(v), (bad & 2u) ? 0.f : pk_hi(v));
+
+// RK2 trace from a face centre (FACE = 0, 1, 2: the +x, +y, +z face) or the cell centre
+// (FACE = 3) and the sample of field RF at the departure point, for both cells of a thread.
+// (mx, my, mz) = half-step offsets from stage 0.  Sampling component b from a point of type a
+// shifts axis a by +1/2 (a face only) and axis b by -1/2 unless a = b (SURVEY A.2 intended).
+template <int NW, int FACE>
+__device__ __forceinline__ pk2 adv_trace2(const float* __restrict__ RU, const float* __restrict__ RV,
+                                          const float* __restrict__ RW, const float* __restrict__ RF,
+                                          unsigned tbm, unsigned kcm, pk2 mx, pk2 my, pk2 mz,
+                                          pk2 cc, pk2 magic, unsigned& bad) {
+  const pk2 ph = pk(0.5f, 0.5f), nh = pk(-0.5f, -0.5f);
+  bad |= adv_bad2(mx, my, mz, ADV_MAXOFF - 0.5f);
+  const AdvAx2 P0 = adv_split2(mx, magic), P1 = adv_split2(my, magic), P2 = adv_split2(mz, magic);
+  const AdvAx2 Q0 = adv_split2(pk_add(mx, FACE == 0 ? ph : nh), magic);
+  const AdvAx2 Q1 = adv_split2(pk_add(my, FACE == 1 ? ph : nh), magic);
+  const AdvAx2 Q2 = adv_split2(pk_add(mz, FACE == 2 ? ph : nh), magic);
+#define ADV_VAR(comp, axis) \
+  (((FACE < 3 && (axis) == FACE && (comp) != FACE) || ((axis) == (comp) && (comp) != FACE)))
+  const pk2 u1 = adv_tri2<NW>(RU, tbm, kcm, ADV_VAR(0, 0) ? Q0 : P0, ADV_VAR(0, 1) ? Q1 : P1,
+                              ADV_VAR(0, 2) ? Q2 : P2);
+  const pk2 v1 = adv_tri2<NW>(RV, tbm, kcm, ADV_VAR(1, 0) ? Q0 : P0, ADV_VAR(1, 1) ? Q1 : P1,
+                              ADV_VAR(1, 2) ? Q2 : P2);
+  const pk2 w1 = adv_tri2<NW>(RW, tbm, kcm, ADV_VAR(2, 0) ? Q0 : P0, ADV_VAR(2, 1) ? Q1 : P1,
+                              ADV_VAR(2, 2) ? Q2 : P2);
+#undef ADV_VAR
+  const pk2 dx = pk_mul(cc, u1), dy = pk_mul(cc, v1), dz = pk_mul(cc, w1);
+  bad |= adv_bad2(dx, dy, dz, ADV_MAXOFF);
+  return adv_tri2<NW>(RF, tbm, kcm, adv_split2(dx, magic), adv_split2(dy, magic),
+                      adv_split2(dz, magic));
 }
 
 // VEL = 1: u, v, w -> o0, o1, o2.  NSC = 1: one cell-centred scalar (fourth staged field -> os).
@@ -221,140 +251,81 @@ k_advect_tma(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ C
   const float* __restrict__ RV = &sm_.ring[1][0][0];
   const float* __restrict__ RW = &sm_.ring[2][0][0];
   const float* __restrict__ RS = &sm_.ring[NF - 1][0][0];
-  const unsigned tb = (unsigned)((ty + 3) * ROW + lane + 4);         // first cell in the raw tile
-  const unsigned tbm = tb - ADVT_MAGIC_I * (unsigned)(ROW + 1);
+  const int tb = (ty + 3) * ROW + lane + 4;                          // first cell in the raw tile
+  const unsigned tbm = (unsigned)tb - ADVT_MAGIC_I * (unsigned)(ROW + 1);
   const pk2 magic = pk(ADVT_MAGIC, ADVT_MAGIC);
-  const pk2 hh = pk(0.5f, 0.5f), nh = pk(-0.5f, -0.5f), qd = pk(0.25f, 0.25f);
+  const pk2 hh = pk(0.5f, 0.5f), qd = pk(0.25f, 0.25f);
   const pk2 cc = pk(c, c), hc = pk(0.5f * c, 0.5f * c);
-  const float lim1 = ADV_MAXOFF - 0.5f, lim2 = ADV_MAXOFF;
   const long long dbg = (long long)NW * g.nx;                        // second cell in global memory
   long long idx = ((long long)kb * g.ny + ja) * g.nx + i;
+#define LD2(R, a, off) pk((R)[(a) + (off)], (R)[(a) + DB + (off)])
+
+  // stage-0 values that a plane hands to the next one (plane k+1 of this iteration is plane k
+  // of the next): primed here for k = kb
+  for (int p = pfirst; p <= kb + 2; ++p)
+    mbar_wait_bounded(&sm_.full[slot_of(p)], 0u);
+  pk2 u_c, u_xm, v_c, v_ym, w_zm, w_zm_xp, w_zm_yp;
+  {
+    const int a0 = slot_of(kb) * PL + tb, am = slot_of(kb - 1) * PL + tb;
+    u_c = LD2(RU, a0, 0); u_xm = LD2(RU, a0, -1);
+    v_c = LD2(RV, a0, 0); v_ym = LD2(RV, a0, -ROW);
+    w_zm = LD2(RW, am, 0); w_zm_xp = LD2(RW, am, 1); w_zm_yp = LD2(RW, am, ROW);
+  }
+  unsigned med_a = act_a ? media[idx] : (unsigned)SOLID;
+  unsigned med_b = act_b ? media[idx + dbg] : (unsigned)SOLID;
 
   for (int k = kb; k < ke; ++k, idx += g.plane) {
-    for (int p = (k == kb) ? pfirst : k + 3; p <= k + 3; ++p)
-      mbar_wait_bounded(&sm_.full[slot_of(p)], (unsigned)((p - pfirst) >> 3) & 1u);
-    const bool fl_a = act_a && media[idx] == FLUID;
-    const bool fl_b = act_b && media[idx + dbg] == FLUID;
+    mbar_wait_bounded(&sm_.full[slot_of(k + 3)], (unsigned)((k + 3 - pfirst) >> 3) & 1u);
+    const bool fl_a = med_a == FLUID, fl_b = med_b == FLUID;
+    if (k + 1 < ke) {                        // labels of the next plane: a global-memory latency
+      if (act_a) med_a = media[idx + g.plane];
+      if (act_b) med_b = media[idx + g.plane + dbg];
+    }
     const unsigned kcm = (unsigned)(k + 64) - ADVT_MAGIC_I;
-    const unsigned a0 = (unsigned)slot_of(k) * PL + tb;
-    const unsigned am = (unsigned)slot_of(k - 1) * PL + tb;
-    const unsigned ap = (unsigned)slot_of(k + 1) * PL + tb;
-#define LD2(R, a, off) pk((R)[(a) + (off)], (R)[(a) + DB + (off)])
-    const pk2 u00 = LD2(RU, a0, 0), v00 = LD2(RV, a0, 0), w00 = LD2(RW, a0, 0);
+    const int a0 = slot_of(k) * PL + tb;
+    const int ap = slot_of(k + 1) * PL + tb;
+    const pk2 u00 = u_c, v00 = v_c, u_m = u_xm, v_m = v_ym;
+    const pk2 w00 = LD2(RW, a0, 0), w_xp = LD2(RW, a0, 1), w_yp = LD2(RW, a0, ROW);
+    const pk2 u_zp = LD2(RU, ap, 0), u_zp_xm = LD2(RU, ap, -1);
+    const pk2 v_zp = LD2(RV, ap, 0), v_zp_ym = LD2(RV, ap, -ROW);
     pk2 s00 = 0;
     if (NSC) s00 = LD2(RS, a0, 0);
     pk2 nu = u00, nv = v00, nw = w00, ns = s00;
     unsigned bad = 0;                        // cells that go to the worklist
-    // warp-uniform: the votes below need every lane (lanes without a Fluid cell compute on
-    // in-range staged data and discard the result)
+    // warp-uniform: lanes without a Fluid cell compute on staged data and discard the result
     if (__any_sync(0xffffffffu, fl_a || fl_b)) {
       if (VEL) {
-        // ---- U face at (i + 1/2, j, k): closed-form stage 0, stage 1 at the midpoint
-        {
-          const pk2 v0 = pk_mul(qd, pk_add(pk_add(LD2(RV, a0, -ROW), v00),
+        {   // U face at (i + 1/2, j, k): closed-form stage 0 (v, w averaged over 4 faces)
+          const pk2 v0 = pk_mul(qd, pk_add(pk_add(v_m, v00),
                                            pk_add(LD2(RV, a0, -ROW + 1), LD2(RV, a0, 1))));
-          const pk2 w0 = pk_mul(qd, pk_add(pk_add(LD2(RW, am, 0), w00),
-                                           pk_add(LD2(RW, am, 1), LD2(RW, a0, 1))));
-          pk2 mx = pk_mul(hc, u00), my = pk_mul(hc, v0), mz = pk_mul(hc, w0);
-          unsigned b1 = adv_bad2(mx, my, mz, lim1);
-          if (__any_sync(0xffffffffu, b1)) {
-            mx = adv_zero_bad(mx, b1); my = adv_zero_bad(my, b1); mz = adv_zero_bad(mz, b1);
-          }
-          const AdvAx2 X0 = adv_split2(mx, magic), X1 = adv_split2(pk_add(mx, hh), magic);
-          const AdvAx2 Y0 = adv_split2(my, magic), Y1 = adv_split2(pk_add(my, nh), magic);
-          const AdvAx2 Z0 = adv_split2(mz, magic), Z1 = adv_split2(pk_add(mz, nh), magic);
-          const pk2 u1 = adv_tri2<NW>(RU, tbm, kcm, X0, Y0, Z0);
-          const pk2 v1 = adv_tri2<NW>(RV, tbm, kcm, X1, Y1, Z0);
-          const pk2 w1 = adv_tri2<NW>(RW, tbm, kcm, X1, Y0, Z1);
-          pk2 dx = pk_mul(cc, u1), dy = pk_mul(cc, v1), dz = pk_mul(cc, w1);
-          b1 |= adv_bad2(dx, dy, dz, lim2);
-          if (__any_sync(0xffffffffu, b1)) {
-            dx = adv_zero_bad(dx, b1); dy = adv_zero_bad(dy, b1); dz = adv_zero_bad(dz, b1);
-          }
-          nu = adv_tri2<NW>(RU, tbm, kcm, adv_split2(dx, magic), adv_split2(dy, magic),
-                            adv_split2(dz, magic));
-          bad |= b1;
+          const pk2 w0 = pk_mul(qd, pk_add(pk_add(w_zm, w00), pk_add(w_zm_xp, w_xp)));
+          nu = adv_trace2<NW, 0>(RU, RV, RW, RU, tbm, kcm, pk_mul(hc, u00), pk_mul(hc, v0),
+                                 pk_mul(hc, w0), cc, magic, bad);
         }
-        // ---- V face at (i, j + 1/2, k)
-        {
-          const pk2 u0 = pk_mul(qd, pk_add(pk_add(LD2(RU, a0, -1), LD2(RU, a0, ROW - 1)),
+        {   // V face at (i, j + 1/2, k)
+          const pk2 u0 = pk_mul(qd, pk_add(pk_add(u_m, LD2(RU, a0, ROW - 1)),
                                            pk_add(u00, LD2(RU, a0, ROW))));
-          const pk2 w0 = pk_mul(qd, pk_add(pk_add(LD2(RW, am, 0), w00),
-                                           pk_add(LD2(RW, am, ROW), LD2(RW, a0, ROW))));
-          pk2 mx = pk_mul(hc, u0), my = pk_mul(hc, v00), mz = pk_mul(hc, w0);
-          unsigned b1 = adv_bad2(mx, my, mz, lim1);
-          if (__any_sync(0xffffffffu, b1)) {
-            mx = adv_zero_bad(mx, b1); my = adv_zero_bad(my, b1); mz = adv_zero_bad(mz, b1);
-          }
-          const AdvAx2 X0 = adv_split2(mx, magic), X1 = adv_split2(pk_add(mx, nh), magic);
-          const AdvAx2 Y0 = adv_split2(my, magic), Y1 = adv_split2(pk_add(my, hh), magic);
-          const AdvAx2 Z0 = adv_split2(mz, magic), Z1 = adv_split2(pk_add(mz, nh), magic);
-          const pk2 u1 = adv_tri2<NW>(RU, tbm, kcm, X1, Y1, Z0);
-          const pk2 v1 = adv_tri2<NW>(RV, tbm, kcm, X0, Y0, Z0);
-          const pk2 w1 = adv_tri2<NW>(RW, tbm, kcm, X0, Y1, Z1);
-          pk2 dx = pk_mul(cc, u1), dy = pk_mul(cc, v1), dz = pk_mul(cc, w1);
-          b1 |= adv_bad2(dx, dy, dz, lim2);
-          if (__any_sync(0xffffffffu, b1)) {
-            dx = adv_zero_bad(dx, b1); dy = adv_zero_bad(dy, b1); dz = adv_zero_bad(dz, b1);
-          }
-          nv = adv_tri2<NW>(RV, tbm, kcm, adv_split2(dx, magic), adv_split2(dy, magic),
-                            adv_split2(dz, magic));
-          bad |= b1;
+          const pk2 w0 = pk_mul(qd, pk_add(pk_add(w_zm, w00), pk_add(w_zm_yp, w_yp)));
+          nv = adv_trace2<NW, 1>(RU, RV, RW, RV, tbm, kcm, pk_mul(hc, u0), pk_mul(hc, v00),
+                                 pk_mul(hc, w0), cc, magic, bad);
         }
-        // ---- W face at (i, j, k + 1/2)
-        {
-          const pk2 u0 = pk_mul(qd, pk_add(pk_add(LD2(RU, a0, -1), LD2(RU, ap, -1)),
-                                           pk_add(u00, LD2(RU, ap, 0))));
-          const pk2 v0 = pk_mul(qd, pk_add(pk_add(LD2(RV, a0, -ROW), LD2(RV, ap, -ROW)),
-                                           pk_add(v00, LD2(RV, ap, 0))));
-          pk2 mx = pk_mul(hc, u0), my = pk_mul(hc, v0), mz = pk_mul(hc, w00);
-          unsigned b1 = adv_bad2(mx, my, mz, lim1);
-          if (__any_sync(0xffffffffu, b1)) {
-            mx = adv_zero_bad(mx, b1); my = adv_zero_bad(my, b1); mz = adv_zero_bad(mz, b1);
-          }
-          const AdvAx2 X0 = adv_split2(mx, magic), X1 = adv_split2(pk_add(mx, nh), magic);
-          const AdvAx2 Y0 = adv_split2(my, magic), Y1 = adv_split2(pk_add(my, nh), magic);
-          const AdvAx2 Z0 = adv_split2(mz, magic), Z1 = adv_split2(pk_add(mz, hh), magic);
-          const pk2 u1 = adv_tri2<NW>(RU, tbm, kcm, X1, Y0, Z1);
-          const pk2 v1 = adv_tri2<NW>(RV, tbm, kcm, X0, Y1, Z1);
-          const pk2 w1 = adv_tri2<NW>(RW, tbm, kcm, X0, Y0, Z0);
-          pk2 dx = pk_mul(cc, u1), dy = pk_mul(cc, v1), dz = pk_mul(cc, w1);
-          b1 |= adv_bad2(dx, dy, dz, lim2);
-          if (__any_sync(0xffffffffu, b1)) {
-            dx = adv_zero_bad(dx, b1); dy = adv_zero_bad(dy, b1); dz = adv_zero_bad(dz, b1);
-          }
-          nw = adv_tri2<NW>(RW, tbm, kcm, adv_split2(dx, magic), adv_split2(dy, magic),
-                            adv_split2(dz, magic));
-          bad |= b1;
+        {   // W face at (i, j, k + 1/2)
+          const pk2 u0 = pk_mul(qd, pk_add(pk_add(u_m, u_zp_xm), pk_add(u00, u_zp)));
+          const pk2 v0 = pk_mul(qd, pk_add(pk_add(v_m, v_zp_ym), pk_add(v00, v_zp)));
+          nw = adv_trace2<NW, 2>(RU, RV, RW, RW, tbm, kcm, pk_mul(hc, u0), pk_mul(hc, v0),
+                                 pk_mul(hc, w00), cc, magic, bad);
         }
       }
-      if (NSC) {
-        // ---- cell-centred scalar: the same RK2 trace from the cell centre (i, j, k)
-        const pk2 u0 = pk_mul(hh, pk_add(LD2(RU, a0, -1), u00));
-        const pk2 v0 = pk_mul(hh, pk_add(LD2(RV, a0, -ROW), v00));
-        const pk2 w0 = pk_mul(hh, pk_add(LD2(RW, am, 0), w00));
-        pk2 mx = pk_mul(hc, u0), my = pk_mul(hc, v0), mz = pk_mul(hc, w0);
-        unsigned b1 = adv_bad2(mx, my, mz, lim1);
-        if (__any_sync(0xffffffffu, b1)) {
-          mx = adv_zero_bad(mx, b1); my = adv_zero_bad(my, b1); mz = adv_zero_bad(mz, b1);
-        }
-        const AdvAx2 X0 = adv_split2(mx, magic), X1 = adv_split2(pk_add(mx, nh), magic);
-        const AdvAx2 Y0 = adv_split2(my, magic), Y1 = adv_split2(pk_add(my, nh), magic);
-        const AdvAx2 Z0 = adv_split2(mz, magic), Z1 = adv_split2(pk_add(mz, nh), magic);
-        const pk2 u1 = adv_tri2<NW>(RU, tbm, kcm, X1, Y0, Z0);
-        const pk2 v1 = adv_tri2<NW>(RV, tbm, kcm, X0, Y1, Z0);
-        const pk2 w1 = adv_tri2<NW>(RW, tbm, kcm, X0, Y0, Z1);
-        pk2 dx = pk_mul(cc, u1), dy = pk_mul(cc, v1), dz = pk_mul(cc, w1);
-        b1 |= adv_bad2(dx, dy, dz, lim2);
-        if (__any_sync(0xffffffffu, b1)) {
-          dx = adv_zero_bad(dx, b1); dy = adv_zero_bad(dy, b1); dz = adv_zero_bad(dz, b1);
-        }
-        ns = adv_tri2<NW>(RS, tbm, kcm, adv_split2(dx, magic), adv_split2(dy, magic),
-                          adv_split2(dz, magic));
-        bad |= b1;
+      if (NSC) {   // cell-centred scalar: velocity at the centre = mean of the two faces
+        const pk2 u0 = pk_mul(hh, pk_add(u_m, u00));
+        const pk2 v0 = pk_mul(hh, pk_add(v_m, v00));
+        const pk2 w0 = pk_mul(hh, pk_add(w_zm, w00));
+        ns = adv_trace2<NW, 3>(RU, RV, RW, RS, tbm, kcm, pk_mul(hc, u0), pk_mul(hc, v0),
+                               pk_mul(hc, w0), cc, magic, bad);
       }
     }
-#undef LD2
+    u_c = u_zp; u_xm = u_zp_xm; v_c = v_zp; v_ym = v_zp_ym;
+    w_zm = w00; w_zm_xp = w_xp; w_zm_yp = w_yp;
     // non-Fluid cells keep their values (Convection.fs:60-61 maps over markers); flagged cells
     // keep them until k_advect_rest has recomputed them
     const bool take_a = fl_a && !(bad & 1u), take_b = fl_b && !(bad & 2u);
@@ -380,6 +351,7 @@ k_advect_tma(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ C
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm_.empty[(k - kb) & 1]);
   }
+#undef LD2
 }
 
 }  // namespace spl
