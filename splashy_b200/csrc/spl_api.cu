@@ -96,6 +96,59 @@ thread_local std::string g_create_error;
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+// ---- peer-to-peer exchange of the per-rank scalars (world > 1) ------------------------------
+// Every rank owns a PeerBox that the other ranks of the node map through CUDA IPC.  A gather
+// is one tiny kernel: thread w stores this rank's value(s) and then the sequence number of the
+// gather into rank w's box (release: __threadfence_system between the two), then waits for
+// rank w's stamp in its own box and copies the value into the local slot array.  A rank
+// writes before it waits, so no rank depends on a kernel that has not been launched yet by its
+// own stream.  Four value slots indexed by the sequence number: a rank is at most one gather
+// ahead of the slowest one.  The box is never reset by the host (a reset could race with a
+// faster peer's store).
+struct PeerBox {
+  double val[4][MAXW][2];
+  unsigned long long seq[4][MAXW];
+};
+struct PeerShared {        // one IPC-shared allocation per rank
+  PeerBox gather;
+  FusedBox fused;
+};
+struct PeerPtrs {
+  PeerBox* p[MAXW];
+};
+
+__global__ void k_peer_gather(PeerPtrs peers, int rank, int world, unsigned long long seq,
+                              double* __restrict__ slots, int per_rank) {
+  const int w = threadIdx.x;
+  if (w >= world) return;
+  const int b = (int)(seq & 3ull);
+  const double v0 = slots[rank * per_rank];
+  const double v1 = per_rank > 1 ? slots[rank * per_rank + 1] : 0.0;
+  if (w != rank) {
+    PeerBox* dst = peers.p[w];
+    volatile double* dv = &dst->val[b][rank][0];
+    dv[0] = v0;
+    dv[1] = v1;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&dst->seq[b][rank]) = seq;
+    PeerBox* mine = peers.p[rank];
+    volatile unsigned long long* f = &mine->seq[b][w];
+    unsigned long long t0 = 0;
+    for (unsigned spin = 1; *f != seq; ++spin) {
+      if ((spin & 1023u) == 0u) {        // a missing rank must abort the launch, not hang the GPU
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 8000000000ull) __trap();
+      }
+    }
+    __threadfence_system();
+    volatile double* sv = &mine->val[b][w][0];
+    slots[w * per_rank] = sv[0];
+    if (per_rank > 1) slots[w * per_rank + 1] = sv[1];
+  }
+}
+
 struct MgLevel {
   Geo g{};
   uint8_t *media = nullptr, *codes = nullptr;   // plane-0 pointers
@@ -133,8 +186,28 @@ struct spl_ctx {
   int* flag = nullptr;         // device int (quirk "too far")
   int* hflag = nullptr;        // pinned
   int* hdone = nullptr;        // pinned [2]: lagged convergence poll
+  double* hagree = nullptr;    // pinned [MAXW + 1]: agree_max
   cudaEvent_t dev[2]{};
   ncclComm_t comm = nullptr;
+  // z-slabs: the direction halo travels on a second (high-priority) stream while the interior
+  // chunks of phase A run (SPL_OVERLAP=0: everything on one stream); the per-rank CG scalars
+  // are exchanged by peer-to-peer stores into IPC-mapped boxes (SPL_P2P=0: ncclAllGather)
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_beta = nullptr, ev_halo = nullptr;
+  bool overlap = true;
+  bool split = false;          // SPL_SPLIT=1: interior / boundary launches of phase A around NCCL send / recv
+  bool p2p = false;
+  PeerShared* pbox = nullptr;
+  PeerPtrs peers{};
+  FusedBox* fboxes[MAXW]{};    // every rank's FusedBox (own + IPC-mapped)
+  void* peer_maps[MAXW]{};     // IPC mappings to close
+  char* nb_sbuf[2][MAX_SBUF]{};   // the neighbours' (below / above) direction buffers, allocation starts
+  void* nb_maps[2][MAX_SBUF]{};
+  bool fused_ok = false;       // the PCG iteration runs over peer memory (SPL_FUSED=0: separate gathers)
+  unsigned long long pseq = 0;
+  unsigned long long iter_seq = 0;
+  unsigned* hticket = nullptr;
+  std::vector<int> slab_geo;   // world > 1: {nz, z0} of every rank
   bool uploaded = false, have_rhs = false, have_snapshot = false;
   int fixed_iters = 0;
   // iterative refinement: after a converged solve, restart PCG from the true fp64 residual
@@ -256,8 +329,10 @@ ncclDataType_t nccl_real(const spl_ctx* c) {
 }
 
 // exchange `width` z-planes of a field with both slab neighbours
-int exchange_halo(spl_ctx* c, char* plane0, size_t es, ncclDataType_t ty, int width) {
+int exchange_halo(spl_ctx* c, char* plane0, size_t es, ncclDataType_t ty, int width,
+                  cudaStream_t st = nullptr) {
   if (c->d.world <= 1) return SPL_OK;
+  if (!st) st = c->stream;
   const Geo& g = c->g;
   if (width > g.hz) width = g.hz;
   if (width > g.nz) width = g.nz;
@@ -265,13 +340,13 @@ int exchange_halo(spl_ctx* c, char* plane0, size_t es, ncclDataType_t ty, int wi
   const size_t pb = (size_t)g.plane * es;
   NC(g_nccl.GroupStart());
   if (c->d.rank > 0) {
-    NC(g_nccl.Send(plane0, cnt, ty, c->d.rank - 1, c->comm, c->stream));
-    NC(g_nccl.Recv(plane0 - (size_t)width * pb, cnt, ty, c->d.rank - 1, c->comm, c->stream));
+    NC(g_nccl.Send(plane0, cnt, ty, c->d.rank - 1, c->comm, st));
+    NC(g_nccl.Recv(plane0 - (size_t)width * pb, cnt, ty, c->d.rank - 1, c->comm, st));
   }
   if (c->d.rank < c->d.world - 1) {
     NC(g_nccl.Send(plane0 + (size_t)(g.nz - width) * pb, cnt, ty, c->d.rank + 1, c->comm,
-                   c->stream));
-    NC(g_nccl.Recv(plane0 + (size_t)g.nz * pb, cnt, ty, c->d.rank + 1, c->comm, c->stream));
+                   st));
+    NC(g_nccl.Recv(plane0 + (size_t)g.nz * pb, cnt, ty, c->d.rank + 1, c->comm, st));
   }
   NC(g_nccl.GroupEnd());
   return SPL_OK;
@@ -306,8 +381,32 @@ int exchange_velocity(spl_ctx* c, int width) {
 // complete the per-rank slots of the PCG scalars on every rank
 int gather_slots(spl_ctx* c, double* slots, int per_rank) {
   if (c->d.world <= 1) return SPL_OK;
+  if (c->p2p) {
+    k_peer_gather<<<1, 32, 0, c->stream>>>(c->peers, c->d.rank, c->d.world, ++c->pseq, slots,
+                                           per_rank);
+    c->launches++;
+    return SPL_OK;
+  }
   NC(g_nccl.AllGather(slots + (size_t)c->d.rank * per_rank, slots, per_rank, ncclDouble,
                       c->comm, c->stream));
+  return SPL_OK;
+}
+
+// world > 1: the maximum over all ranks of a per-rank value (one collective; every rank must
+// call it).  Used to agree on an error before any rank returns early: a rank that left while
+// the others went on into the next halo exchange would leave them waiting for ever.
+int agree_max(spl_ctx* c, double v, double* out) {
+  *out = v;
+  if (c->d.world <= 1) return SPL_OK;
+  c->hagree[MAXW] = v;
+  CU(cudaMemcpyAsync(&c->sc->gD[c->d.rank], &c->hagree[MAXW], sizeof(double),
+                     cudaMemcpyHostToDevice, c->stream));
+  int rc = gather_slots(c, c->sc->gD, 1);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->hagree, c->sc->gD, sizeof(double) * c->d.world, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int w = 0; w < c->d.world; ++w) *out = fmax(*out, c->hagree[w]);
   return SPL_OK;
 }
 
@@ -340,7 +439,7 @@ __global__ void k_finalize(Scal* sc, int par_last) {
 // planes each phase-A CTA marches through.  Long chunks amortise the pipeline
 // prologue (2-3 extra planes of loads per chunk), short ones give more CTAs and a
 // smaller tail; ~2048 CTAs (4-5 waves at 3 CTAs/SM) measured best at 512^3
-// (profiles/r1_phaseA_zchunk.md).
+// (z-chunk sweep in profiles/README.md).
 int phaseA_zchunk(const spl_ctx* c, int tiles_xy) {
   if (c->zchunk_override > 0) return c->zchunk_override;
   const int nz = c->g.nz;
@@ -350,7 +449,7 @@ int phaseA_zchunk(const spl_ctx* c, int tiles_xy) {
   int zc = (nz + gz - 1) / gz;
   if (zc < 8) zc = 8;
   if (zc > nz) zc = nz;
-  while ((long long)tiles_xy * ((nz + zc - 1) / zc) > MAX_PARTIALS) zc *= 2;
+  while (zc < nz && (long long)tiles_xy * ((nz + zc - 1) / zc) > MAX_PARTIALS) zc *= 2;
   return zc;
 }
 
@@ -570,10 +669,18 @@ struct Impl {
 
   // fp32 / VEC = 4 uses the cp.async ring kernel; every other
   // combination (fp64, ragged nx) the register-pipelined generic kernel.
+  // zb0 / zstr / nbt: z-chunks zb0 + blockIdx.z * zstr of a phase of nbt CTAs in total (the
+  // TMA kernel only; every other variant runs the whole grid in one launch)
+  static bool phaseA_splits(const spl_ctx* c) {
+    return std::is_same<T, float>::value && c->use_tma && !c->no_ring && !c->no_ws &&
+           c->g.nx % 16 == 0 && c->vec == 4;
+  }
   template <int VEC, int PC>
   static void launch_phaseA(spl_ctx* c, dim3 gridA, dim3 blockA, const T* zr, const T* sold,
-                            T* snew, int par, int zc) {
+                            T* snew, int par, int zc, int zb0 = 0, int zstr = 1,
+                            unsigned nbt = 0, const Fused& fz = Fused{}) {
     const Geo& g = c->g;
+    if (nbt == 0) nbt = gridA.x * gridA.y * gridA.z;
     if constexpr (std::is_same<T, float>::value && VEC == 4) {
       if (c->use_tma && !c->no_ring && !c->no_ws && g.nx % 16 == 0) {   // TMA producer warp
         const CUtensorMap* mz = tensor_map_for(c, g, zr, TM_F);
@@ -587,7 +694,8 @@ struct Impl {
             c->ring_attr_set |= (256 << PC);
           }
           k_phaseA_tma<PC><<<gridA, dim3(32, TILE_Y + 1), sizeof(TmaSmem), c->stream>>>(
-              *mz, *mo, *mn, *mc, g, c->codes, zr, sold, snew, P(c->q), c->sc, c->partials, par, zc);
+              *mz, *mo, *mn, *mc, g, c->codes, zr, sold, snew, P(c->q), c->sc, c->partials, par, zc,
+              zb0, zstr, nbt, fz);
           c->launches++;
           return;
         }
@@ -632,7 +740,7 @@ struct Impl {
     int zc = (v.nz + gz - 1) / gz;
     if (zc < 16) zc = 16;
     if (zc > v.nz) zc = v.nz;
-    while ((long long)tx * ((v.nz + zc - 1) / zc) > MAX_PARTIALS) zc *= 2;
+    while (zc < v.nz && (long long)tx * ((v.nz + zc - 1) / zc) > MAX_PARTIALS) zc *= 2;
     const dim3 grid(tx, 1, (v.nz + zc - 1) / zc);
     LAUNCH(c, (k_phaseA<T, VEC, PC, 1>), grid, dim3(32, 1), v, c->codes, zr, sold, snew,
            P(c->q), c->sc, c->partials, par, zc);
@@ -839,8 +947,10 @@ struct Impl {
       const int zlo = k.g.z0 > 0 ? k.g.z0 - 1 : 0;
       const int zhi = (k.g.z0 + k.g.nz < gg.nz) ? k.g.z0 + k.g.nz + 1 : gg.nz;
       const size_t pb = (size_t)gg.plane * sizeof(T);
-      cudaMemcpyAsync(k.u + ((long long)zlo - k.g.z0) * (long long)pb, c->mg_gu + (size_t)zlo * pb,
-                      (size_t)(zhi - zlo) * pb, cudaMemcpyDeviceToDevice, c->stream);
+      if (cudaMemcpyAsync(k.u + ((long long)zlo - k.g.z0) * (long long)pb,
+                          c->mg_gu + (size_t)zlo * pb, (size_t)(zhi - zlo) * pb,
+                          cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess && xrc == SPL_OK)
+        xrc = fail(c, SPL_E_CUDA, "copy of the global coarsest solution failed");
       cur[L - 1] = k.u;
     } else if (lb < L) {
       MgBottomArgs<T> a{};
@@ -963,7 +1073,7 @@ struct Impl {
 
     // rho_0 = r.z, max|b|  (phase B with alpha = 0)
     LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
-           c->sc, c->partials, 0, 1, m);
+           c->sc, c->partials, 0, 1, m, Fused{});
     int rc = SPL_OK;
     if (pc_explicit_z(PC) && (rc = precondition(c, 0))) return rc;
     if ((rc = gather_slots(c, &c->sc->gBM[0][0][0], 2))) return rc;
@@ -977,6 +1087,12 @@ struct Impl {
     int batch = 0;
     bool done = false;
     const int poll = (PC == PC_MG) ? 1 : 16;   // an MG iteration is ~70 launches
+    Fused fz{};
+    for (int w = 0; w < c->d.world && w < MAXW; ++w) fz.box[w] = c->fboxes[w];
+    if (const char* e = getenv("SPL_FUSED_MODE")) fz.mode = atoi(e);
+    const bool send_on_main = (fz.mode & 2) != 0;
+    bool fused_prev = false;       // the previous iteration's phase B pushed its slots to the peers
+    unsigned long long last_stamp = 0;
     while (it < limit && !done) {
       const int stop = (it + poll < limit) ? it + poll : limit;
       for (; it < stop;) {
@@ -984,27 +1100,84 @@ struct Impl {
         const int par = it & 1;
         char* sold = c->sbuf[(it - 1) % m];   // s_{it-1}
         char* snew = c->sbuf[it % m];         // s_it
-        if (c->d.world > 1) {
-          LAUNCH(c, (k_dir_boundary<T, PC>), grid_for(c, 2 * g.plane), 256, g, c->codes, zr,
-                 P(sold), P(snew), c->sc, par);
-          if ((rc = exchange_halo(c, snew, sizeof(T), nccl_real(c), 1))) return rc;
-        }
+        const bool two_d = g.nz == 1 && g.nzg == 1 && g.ny > 1 && !c->no_2d_view;
         const bool prof = c->profile_iters > 0 && it <= c->profile_iters;
+        // z-slabs, three ways to get the boundary planes of s' to the neighbours:
+        //  fused  the iteration runs over peer memory: k_send_boundary stores the planes into the
+        //         neighbours' halos on the side stream, phase A is ONE launch whose boundary
+        //         chunks come last and wait for the neighbour's stamp, the CG scalars travel
+        //         as peer stores from the last CTA of each phase -- no NCCL call, no extra launch
+        //  split  NCCL send / recv on the side stream while the interior chunks of phase A run
+        //         (SPL_SPLIT=1; loses to the plain order at 512^3: the boundary launch is a
+        //         1.15-wave tail)
+        //  plain  boundary planes, send / recv, phase A, all on one stream
+        const bool tma_ok = c->d.world > 1 && c->cstream && !two_d && phaseA_splits(c);
+        const bool fused = tma_ok && c->fused_ok && !pc_explicit_z(PC) && gridA.z >= 3;
+        const bool split = tma_ok && !fused && c->split && gridA.z >= 3;
+        const bool fhalo = fused && !(fz.mode & 16);   // 16: scalars over peer memory, halo over NCCL
+        fz.on = fused ? 1 : 0;
+        fz.halo = fhalo ? 1 : 0;
+        if (fused) {
+          fz.stamp = ++c->iter_seq;
+          fz.wait_b = fused_prev ? fz.stamp - 1 : 0;
+          fused_prev = true;
+          last_stamp = fz.stamp;
+        }
+        if (fhalo) {
+          if constexpr (std::is_same<T, float>::value && !pc_explicit_z(PC)) {
+            if (!send_on_main) {
+              CU(cudaEventRecord(c->ev_beta, c->stream));        // r of iteration it-1 is final
+              CU(cudaStreamWaitEvent(c->cstream, c->ev_beta, 0));
+            }
+            const int bi = it % m;
+            const size_t pf = (size_t)g.plane * sizeof(float);
+            float* lo = c->d.rank > 0 ? reinterpret_cast<float*>(
+                c->nb_sbuf[0][bi] + (size_t)(g.hz + c->slab_geo[2 * (c->d.rank - 1)]) * pf) : nullptr;
+            float* hi = c->d.rank < c->d.world - 1 ? reinterpret_cast<float*>(
+                c->nb_sbuf[1][bi] + (size_t)(g.hz - 1) * pf) : nullptr;
+            const int sgrid = grid_for(c, 2 * g.plane / 4) < c->sms ? grid_for(c, 2 * g.plane / 4) : c->sms;
+            k_send_boundary<PC><<<sgrid, 256, 0,
+                                  send_on_main ? c->stream : c->cstream>>>(
+                g, c->codes, zr, P(sold), lo, hi, c->sc, par, fz, c->hticket);
+            c->launches++;
+            if (!send_on_main) CU(cudaEventRecord(c->ev_halo, c->cstream));   // it has read r: phase B may run
+          }
+        } else if (c->d.world > 1) {
+          cudaStream_t hs = split ? c->cstream : c->stream;
+          if (split) {
+            CU(cudaEventRecord(c->ev_beta, c->stream));          // beta of this iteration is complete
+            CU(cudaStreamWaitEvent(c->cstream, c->ev_beta, 0));
+          }
+          k_dir_boundary<T, PC><<<grid_for(c, 2 * g.plane), 256, 0, hs>>>(
+              g, c->codes, zr, P(sold), P(snew), c->sc, par);
+          c->launches++;
+          if ((rc = exchange_halo(c, snew, sizeof(T), nccl_real(c), 1, hs))) return rc;
+          if (split) CU(cudaEventRecord(c->ev_halo, c->cstream));
+        }
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1)], c->stream));
-        if (g.nz == 1 && g.nzg == 1 && g.ny > 1 && !c->no_2d_view)
+        if (two_d) {
           launch_phaseA_2d<VEC, PC>(c, zr, P(sold), P(snew), par);
-        else
-          launch_phaseA<VEC, PC>(c, gridA, blockA, zr, P(sold), P(snew), par, zc);
+        } else if (split) {
+          const unsigned nbt = gridA.x * gridA.y * gridA.z;
+          launch_phaseA<VEC, PC>(c, dim3(gridA.x, gridA.y, gridA.z - 2), blockA, zr, P(sold),
+                                 P(snew), par, zc, 1, 1, nbt);
+          CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+          launch_phaseA<VEC, PC>(c, dim3(gridA.x, gridA.y, 2), blockA, zr, P(sold), P(snew), par,
+                                 zc, 0, (int)gridA.z - 1, nbt);
+        } else {
+          launch_phaseA<VEC, PC>(c, gridA, blockA, zr, P(sold), P(snew), par, zc, 0, 1, 0, fz);
+          if (fhalo && !send_on_main) CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+        }
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 1], c->stream));
-        if ((rc = gather_slots(c, c->sc->gA, 1))) return rc;
+        if (!fz.on && (rc = gather_slots(c, c->sc->gA, 1))) return rc;
         if (prof) CU(cudaEventRecord(c->pev[3 * (it - 1) + 2], c->stream));
         const bool fuse_r = (PC == PC_MG) && mg_fuse_ok(c);
         if (!fuse_r)
           LAUNCH(c, (k_phaseB<T, VEC, PC>), gridB, 256, g, c->codes, P(c->r), P(c->q), P(c->z),
-                 c->sc, c->partials, par, 0, m);
+                 c->sc, c->partials, par, 0, m, fz);
         if (prof) CU(cudaEventRecord(c->pev[3 * c->profile_iters + (it - 1)], c->stream));
         if (pc_explicit_z(PC) && (rc = precondition(c, par, fuse_r))) return rc;   // z = M^-1 r, rho = r.z
-        if ((rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
+        if (!fz.on && (rc = gather_slots(c, &c->sc->gBM[par][0][0], 2))) return rc;
         if (it % m == 0) {   // every buffer holds an unflushed direction: x += sum alpha s
           const bool pf = c->profile_iters > 0 && nflush < 64;
           if (pf) CU(cudaEventRecord(c->xev[2 * nflush], c->stream));
@@ -1027,6 +1200,11 @@ struct Impl {
         done = c->hdone[slot ^ 1] != 0;
       }
       ++batch;
+    }
+    if (fused_prev) {   // slots of the last phase B (k_finalize reads them)
+      fz.on = 1;
+      fz.wait_b = last_stamp;
+      LAUNCH(c, k_fused_wait_B, 1, 32, c->sc, it & 1, fz);
     }
     // terms of the last (K mod m) iterations are still pending
     c->profile_flushes = nflush < 64 ? nflush : 64;
@@ -1192,6 +1370,17 @@ void spl_destroy(spl_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->d.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->cstream) cudaStreamSynchronize(c->cstream);
+  for (int w = 0; w < MAXW; ++w)
+    if (c->peer_maps[w]) cudaIpcCloseMemHandle(c->peer_maps[w]);
+  for (int side = 0; side < 2; ++side)
+    for (int i = 0; i < MAX_SBUF; ++i)
+      if (c->nb_maps[side][i]) cudaIpcCloseMemHandle(c->nb_maps[side][i]);
+  if (c->pbox) cudaFree(c->pbox);
+  if (c->hticket) cudaFree(c->hticket);
+  if (c->cstream) cudaStreamDestroy(c->cstream);
+  if (c->ev_beta) cudaEventDestroy(c->ev_beta);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (void* p : c->alloc)
     if (p) cudaFree(p);
@@ -1212,6 +1401,7 @@ void spl_destroy(spl_ctx* c) {
   if (c->hsc) cudaFreeHost(c->hsc);
   if (c->hflag) cudaFreeHost(c->hflag);
   if (c->hdone) cudaFreeHost(c->hdone);
+  if (c->hagree) cudaFreeHost(c->hagree);
   for (cudaEvent_t e : c->dev)
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev)
@@ -1222,6 +1412,56 @@ void spl_destroy(spl_ctx* c) {
     if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+// z-slabs over peer memory: the two neighbours' direction buffers are mapped through CUDA IPC
+// so that k_send_boundary can store this rank's boundary planes straight into their halos.
+// Every rank exchanges the handles of its nsbuf buffers; the path is used only if every rank
+// mapped what it needs (otherwise: ncclSend / ncclRecv as before).
+static int map_neighbour_sbufs(spl_ctx* c) {
+  const spl_desc& d = c->d;
+  const int m = c->nsbuf;
+  const char* fe = getenv("SPL_FUSED");
+  bool ok = c->p2p && !(fe && atoi(fe) == 0) && d.dtype == SPL_F32;
+  std::vector<unsigned char> hh((size_t)64 * m * d.world, 0);
+  unsigned char* dh = nullptr;
+  CU(cudaMalloc(&dh, hh.size()));
+  for (int i = 0; i < m && ok; ++i) {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, c->alloc[32 + i]) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    memcpy(&hh[((size_t)d.rank * m + i) * 64], &h, 64);
+  }
+  CU(cudaMemcpyAsync(dh + (size_t)d.rank * m * 64, &hh[(size_t)d.rank * m * 64], (size_t)64 * m,
+                     cudaMemcpyHostToDevice, c->stream));
+  NC(g_nccl.AllGather(dh + (size_t)d.rank * m * 64, dh, (size_t)64 * m, ncclUint8, c->comm,
+                      c->stream));
+  CU(cudaMemcpyAsync(hh.data(), dh, hh.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int side = 0; side < 2 && ok; ++side) {
+    const int nb = side == 0 ? d.rank - 1 : d.rank + 1;
+    if (nb < 0 || nb >= d.world) continue;
+    for (int i = 0; i < m; ++i) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, &hh[((size_t)nb * m + i) * 64], 64);
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      c->nb_maps[side][i] = ptr;
+      c->nb_sbuf[side][i] = static_cast<char*>(ptr);
+    }
+  }
+  unsigned char mine = ok, *dm = dh;     // agree: all ranks or none
+  CU(cudaMemcpyAsync(dm + d.rank, &mine, 1, cudaMemcpyHostToDevice, c->stream));
+  NC(g_nccl.AllGather(dm + d.rank, dm, 1, ncclUint8, c->comm, c->stream));
+  CU(cudaMemcpyAsync(hh.data(), dm, d.world, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int w = 0; w < d.world; ++w) ok = ok && hh[w];
+  c->fused_ok = ok;
+  CU(cudaFree(dh));
+  return SPL_OK;
 }
 
 static int create_impl(spl_ctx* c, const spl_desc* desc) {
@@ -1236,6 +1476,9 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
     return fail(c, SPL_E_BADARG, "dtype %d is neither SPL_F32 nor SPL_F64", d.dtype);
   if (!(d.h > 0.0) || !(d.rho > 0.0))
     return fail(c, SPL_E_BADARG, "h and rho must be positive");
+  if ((long long)((d.nx + 127) / 128) * ((d.ny + TILE_Y - 1) / TILE_Y) > MAX_PARTIALS)
+    return fail(c, SPL_E_BADARG, "box %d x %d: more than %d x-y tiles per plane (cut it along y)",
+                d.nx, d.ny, MAX_PARTIALS);
   if (d.world < 1) d.world = 1;
   if (d.world > MAXW) return fail(c, SPL_E_BADARG, "world %d exceeds %d", d.world, MAXW);
   if (d.rank < 0 || d.rank >= d.world)
@@ -1282,6 +1525,94 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
   for (auto& e : c->tev) CU(cudaEventCreate(&e));
+  if (d.world > 1) {
+    std::string err;
+    if (!d.nccl_id) return fail(c, SPL_E_BADARG, "world > 1 needs desc.nccl_id");
+    if (!load_nccl(err)) return fail(c, SPL_E_CUDA, "%s", err.c_str());
+    ncclUniqueId id;
+    memcpy(&id, d.nccl_id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, d.world, id, d.rank));
+    if (const char* e = getenv("SPL_OVERLAP")) c->overlap = atoi(e) != 0;
+    if (const char* e = getenv("SPL_SPLIT")) c->split = atoi(e) != 0;
+    int plo = 0, phi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+    CU(cudaStreamCreateWithPriority(&c->cstream, cudaStreamNonBlocking, phi));
+    CU(cudaEventCreateWithFlags(&c->ev_beta, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    // peer boxes for the CG scalars: allocate, exchange the IPC handles through NCCL, map the
+    // peers' boxes; used only if every rank could map every box
+    const char* pe = getenv("SPL_P2P");
+    const bool want = !(pe && atoi(pe) == 0);
+    CU(cudaMalloc(&c->pbox, sizeof(PeerShared)));
+    CU(cudaMemsetAsync(c->pbox, 0, sizeof(PeerShared), c->stream));
+    CU(cudaMalloc(&c->hticket, sizeof(unsigned)));
+    CU(cudaMemsetAsync(c->hticket, 0, sizeof(unsigned), c->stream));
+    cudaIpcMemHandle_t mine;
+    unsigned char ok = want && cudaIpcGetMemHandle(&mine, c->pbox) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof mine); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    unsigned char* dh = nullptr;
+    CU(cudaMalloc(&dh, (size_t)65 * d.world));
+    std::vector<unsigned char> hh((size_t)65 * d.world, 0);
+    memcpy(&hh[(size_t)65 * d.rank], &mine, 64);
+    hh[(size_t)65 * d.rank + 64] = ok;
+    CU(cudaMemcpyAsync(dh + (size_t)65 * d.rank, &hh[(size_t)65 * d.rank], 65,
+                       cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(dh + (size_t)65 * d.rank, dh, 65, ncclUint8, c->comm, c->stream));
+    CU(cudaMemcpyAsync(hh.data(), dh, hh.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    bool all = true;
+    for (int w = 0; w < d.world; ++w) all = all && hh[(size_t)65 * w + 64];
+    c->peers.p[d.rank] = &c->pbox->gather;
+    c->fboxes[d.rank] = &c->pbox->fused;
+    for (int w = 0; w < d.world && all; ++w) {
+      if (w == d.rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, &hh[(size_t)65 * w], 64);
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        all = false;
+        break;
+      }
+      c->peer_maps[w] = ptr;
+      c->peers.p[w] = &static_cast<PeerShared*>(ptr)->gather;
+      c->fboxes[w] = &static_cast<PeerShared*>(ptr)->fused;
+    }
+    // second round: a rank that failed to map switches everybody back to ncclAllGather
+    unsigned char mapped = all;
+    CU(cudaMemcpyAsync(dh + d.rank, &mapped, 1, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(dh + d.rank, dh, 1, ncclUint8, c->comm, c->stream));
+    CU(cudaMemcpyAsync(hh.data(), dh, d.world, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int w = 0; w < d.world; ++w) all = all && hh[w];
+    c->p2p = all;
+    CU(cudaFree(dh));
+    // slab geometry of every rank (the multigrid hierarchy must coarsen in lock step)
+    int geo[2] = {d.nz, d.z0};
+    int* dg = nullptr;
+    CU(cudaMalloc(&dg, sizeof(int) * 2 * d.world));
+    CU(cudaMemcpyAsync(dg + 2 * d.rank, geo, sizeof geo, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(dg + 2 * d.rank, dg, 2, ncclInt32, c->comm, c->stream));
+    c->slab_geo.resize(2 * d.world);
+    CU(cudaMemcpyAsync(c->slab_geo.data(), dg, sizeof(int) * 2 * d.world, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(dg));
+    int zsum = 0;
+    for (int w = 0; w < d.world; ++w) {
+      if (c->slab_geo[2 * w + 1] != zsum)
+        return fail(c, SPL_E_BADARG, "slab of rank %d starts at plane %d, expected %d", w,
+                    c->slab_geo[2 * w + 1], zsum);
+      zsum += c->slab_geo[2 * w];
+      // the advection halo (hz = 4 planes) comes from the direct neighbour only
+      if (c->slab_geo[2 * w] < 4)
+        return fail(c, SPL_E_BADARG, "slab of rank %d has %d planes: z-slabs need at least 4", w,
+                    c->slab_geo[2 * w]);
+    }
+    if (zsum != d.nz_global)
+      return fail(c, SPL_E_BADARG, "slabs cover %d planes, nz_global is %d", zsum, d.nz_global);
+  }
   int rc;
   char* unused8 = nullptr;
   char* unused9 = nullptr;
@@ -1296,6 +1627,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if (c->nsbuf > MAX_SBUF) c->nsbuf = MAX_SBUF;
   for (int i = 0; i < c->nsbuf; ++i)
     if ((rc = alloc_field(c, 32 + i, c->esz, &c->sbuf[i], 0))) return rc;
+  if (d.world > 1 && (rc = map_neighbour_sbufs(c))) return rc;
   if (d.precond == SPL_PC_RBIC0 || d.precond == SPL_PC_MG) {
     if ((rc = alloc_field(c, 11, c->esz, &c->z, 0))) return rc;
     if ((rc = alloc_field(c, 12, c->esz, &c->einv, 0))) return rc;
@@ -1336,9 +1668,20 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
       if (f.nx > 1 && f.nx < mind) mind = f.nx;
       if (f.ny > 1 && f.ny < mind) mind = f.ny;
       if (f.nz > 1 && f.nz < mind) mind = f.nz;
+      // z-slabs coarsen in lock step: every rank must hold whole coarse planes, and the
+      // decision must be the same on every rank (each level adds collectives to the cycle),
+      // so it is taken from the geometry of ALL slabs at this level
+      if (d.world > 1) {
+        const int lev = (int)c->mg.size() - 1;
+        bool odd = (f.nzg & 1) != 0;
+        for (int w = 0; w < d.world; ++w) {
+          const int wnz = c->slab_geo[2 * w] >> lev, wz0 = c->slab_geo[2 * w + 1] >> lev;
+          if ((wnz & 1) || (wz0 & 1)) odd = true;
+          if (wnz > 1 && wnz < mind) mind = wnz;
+        }
+        if (odd) break;
+      }
       if (mind <= 8 || mind == (1 << 30)) break;
-      // z-slabs coarsen in lock step: every rank must hold whole coarse planes
-      if (d.world > 1 && ((f.nz & 1) || (f.z0 & 1) || (f.nzg & 1))) break;
       MgLevel l;
       l.g.nx = (f.nx + 1) / 2; l.g.ny = (f.ny + 1) / 2; l.g.nz = (f.nz + 1) / 2;
       l.g.hz = 1;
@@ -1386,16 +1729,9 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   CU(cudaHostAlloc(&c->hsc, sizeof(Scal), cudaHostAllocDefault));
   CU(cudaHostAlloc(&c->hflag, sizeof(int), cudaHostAllocDefault));
   CU(cudaHostAlloc(&c->hdone, 2 * sizeof(int), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&c->hagree, (MAXW + 1) * sizeof(double), cudaHostAllocDefault));
   for (auto& e : c->dev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
-  if (d.world > 1) {
-    std::string err;
-    if (!d.nccl_id) return fail(c, SPL_E_BADARG, "world > 1 needs desc.nccl_id");
-    if (!load_nccl(err)) return fail(c, SPL_E_CUDA, "%s", err.c_str());
-    ncclUniqueId id;
-    memcpy(&id, d.nccl_id, 128);
-    NC(g_nccl.CommInitRank(&c->comm, d.world, id, d.rank));
-  }
   c->d.nccl_id = nullptr;   // caller-owned bytes are not kept
   for (int a = 0; a < 3; ++a) c->world.lo[a] = 0;
   c->world.hi[0] = c->g.nx - 1; c->world.hi[1] = c->g.ny - 1; c->world.hi[2] = c->g.nz - 1;
@@ -1526,8 +1862,12 @@ int spl_advect(spl_ctx* c, double dt, spl_info* info) {
     info->trace_escapes = (int64_t)c->hsc->escapes;
     info->kernel_launches = c->launches;
   }
-  if ((c->d.quirks && *c->hflag) || c->hsc->escapes)
-    return fail(c, SPL_E_TRACE, "Backwards particle trace went too far.");   // Convection.fs:65
+  const bool bad = (c->d.quirks && *c->hflag) || c->hsc->escapes;
+  double any = 0.0;
+  if ((rc = agree_max(c, bad ? 1.0 : 0.0, &any))) return rc;
+  if (any > 0.0)   // Convection.fs:65; every rank of a slab decomposition reports it
+    return fail(c, SPL_E_TRACE, bad ? "Backwards particle trace went too far."
+                                    : "Backwards particle trace went too far. (on another rank)");
   return SPL_OK;
 }
 
@@ -1715,8 +2055,14 @@ int spl_step(spl_ctx* c, double dt, spl_info* info) {
 }
 
 // ---- marker stage ---------------------------------------------------------
+static bool integral_h(const spl_ctx* c) {
+  return c->d.h >= 1.0 && c->d.h == std::floor(c->d.h) && c->d.h < 2147483647.0;
+}
+
 static int markers_need(spl_ctx* c, const char* who) {
   if (!c->uploaded) return fail(c, SPL_E_STATE, "%s before spl_upload", who);
+  if (!integral_h(c))   // Coord.nearest works on int<m> (Coord.fs:49-57, Constants.fs:11 h = 10)
+    return fail(c, SPL_E_BADARG, "%s: the marker stage needs an integral cell size h >= 1", who);
   if (c->nmark <= 0) return fail(c, SPL_E_STATE, "%s before spl_set_markers", who);
   if (c->d.world > 1) return fail(c, SPL_E_BADARG, "the marker stage needs world = 1");
   return SPL_OK;
@@ -1740,6 +2086,8 @@ int spl_set_world(spl_ctx* c, const int lo[3], const int hi[3]) {
 int spl_set_markers(spl_ctx* c, int64_t n, const double* xyz) {
   if (!c || n < 0 || (n > 0 && !xyz)) return SPL_E_BADARG;
   if (c->d.world > 1) return fail(c, SPL_E_BADARG, "the marker stage needs world = 1");
+  if (!integral_h(c))
+    return fail(c, SPL_E_BADARG, "spl_set_markers: the marker stage needs an integral cell size h >= 1");
   CU(cudaSetDevice(c->d.device));
   if (c->mloc) { cudaFree(c->mloc); cudaFree(c->mold); cudaFree(c->mnew); }
   c->mloc = nullptr; c->mold = c->mnew = nullptr;
@@ -1892,7 +2240,9 @@ int spl_advance(spl_ctx* c, double dt, int sanity, spl_info* info) {
   if (info) *info = local;
   if (rc) return rc;
   if (sanity) {
-    if (local.nonfinite) return fail(c, SPL_E_NONFINITE, "Invalid pressure.");
+    double nf = 0.0;   // per-rank count: agree before anybody leaves (cleanup has collectives)
+    if ((rc = agree_max(c, local.nonfinite ? 1.0 : 0.0, &nf))) return rc;
+    if (nf > 0.0) return fail(c, SPL_E_NONFINITE, "Invalid pressure.");
     if (local.max_abs_div > 0.0001)   // Pressure.fs:148
       return fail(c, SPL_E_DIVERGENCE, "Velocity field is not correct: divergence %g.",
                   local.max_abs_div);
@@ -2047,6 +2397,12 @@ int spl_profile_pcg(spl_ctx* c, double dt, int iters, float* ms_a, float* ms_b, 
     }
     *ms_a = (float)(a / iters);
     *ms_b = (float)(b / iters);
+    if (getenv("SPL_PROFILE_VERBOSE") && iters > 1) {   // whole iteration period, start to start
+      float t = 0.f;
+      cudaEventElapsedTime(&t, evs[0], evs[3 * (iters - 1)]);
+      fprintf(stderr, "[spl_profile_pcg] rank %d: iteration period %.1f us (phase A %.1f, B %.1f)\n",
+              c->d.rank, 1e3 * t / (iters - 1), 1e3 * a / iters, 1e3 * b / iters);
+    }
     double xs = 0.0;
     for (int i = 0; i < c->profile_flushes; ++i) {
       float t = 0.f;

@@ -52,7 +52,158 @@ struct Scal {
   int flushed;                    // iterations whose alpha s term is already in x
   unsigned ticketA, ticketB, ticketC, ticketX;
   unsigned wl_count;              // advection worklist length
+  // z-slabs over peer memory: stamp up to which the first CTA of a launch has completed gA /
+  // gBM from the peers' boxes (device-local; the other CTAs of the launch poll these)
+  unsigned long long fillA, fillB;
 };
+
+// ---- z-slabs: the PCG iteration over peer memory (NVLink, CUDA IPC) ---------------------------
+// Every rank owns a FusedBox that its peers map.  The last CTA of phase A / phase B stores the
+// rank's partial scalar(s) and then the iteration stamp into every peer's box (release:
+// __threadfence_system between the two); the kernels that consume the scalars wait for the
+// stamps in their OWN box (local memory) and copy the values into the local slot arrays, so
+// every rank still sums the slots in rank order.  A rank never waits for a kernel of its own
+// GPU, and a peer is at most one iteration ahead (it needs this rank's scalars twice per
+// iteration), hence four value slots indexed by the stamp.  hseq: the neighbour below / above
+// has stored its boundary plane of the new search direction into this rank's halo.
+// A scalar travels as ONE 16-byte slot {value, tag} with tag = stamp XOR bits(value): the
+// reader accepts a slot only when tag XOR bits(value) equals the stamp it waits for, so a torn
+// or reordered pair can never be taken for the value of that stamp -- no fence on either side
+// of the exchange, the latency is one NVLink store.
+struct alignas(16) TagSlot {
+  double v;
+  unsigned long long tag;
+};
+struct FusedBox {
+  TagSlot A[4][MAXW];
+  TagSlot B[4][MAXW][2];
+  unsigned long long hseq[2];
+};
+struct Fused {                    // kernel argument
+  FusedBox* box[MAXW];            // box[rank] = this rank's own box
+  unsigned long long stamp;       // this iteration (monotonic over the life of the context)
+  unsigned long long wait_b;      // stamp of the phase B whose slots are still travelling (0: none)
+  int on;                         // 0: the slots are completed by separate gathers
+  int halo;                       // 1: the halo planes arrive as peer stores too (hseq stamps)
+  int mode;                       // experiments (SPL_FUSED_MODE): 1 fence after the poll, 4 no chunk remap
+};
+
+// bounded wait for *f >= want: a missing peer must abort the launch, not hang the GPU.  The
+// poll is an acquire load at system scope (a trailing __threadfence_system in every CTA of a
+// 2000-CTA launch is measurably slower).
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until(const unsigned long long* f, unsigned long long want,
+                                           int fence_mode = 0) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 1; ld_acquire_sys(f) < want; ++spin) {
+    if ((spin & 1023u) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ull) __trap();
+    }
+  }
+  if (fence_mode & 1) __threadfence_system();
+}
+__device__ __forceinline__ void tag_store(TagSlot* p, double v, unsigned long long stamp) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(bits), "l"(bits ^ stamp)
+               : "memory");
+}
+// bounded wait for the slot of `stamp`; returns its value
+__device__ __forceinline__ double tag_wait(const TagSlot* p, unsigned long long stamp) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 1;; ++spin) {
+    unsigned long long bits, tag;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tag) : "l"(p) : "memory");
+    if ((bits ^ tag) == stamp) return __longlong_as_double((long long)bits);
+    if ((spin & 1023u) == 0u) {      // a missing peer must abort the launch, not hang the GPU
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ull) __trap();
+    }
+  }
+}
+// one thread: complete gBM[slot][*] from the peers' phase B of iteration fz.wait_b
+__device__ __forceinline__ void fused_fill_B(const Fused& fz, Scal* sc, int slot) {
+  if (!fz.on || fz.wait_b == 0) return;
+  const FusedBox* mine = fz.box[sc->rank];
+  const int b = (int)(fz.wait_b & 3ull);
+  for (int w = 0; w < sc->world; ++w) {
+    if (w == sc->rank) continue;
+    sc->gBM[slot][w][0] = tag_wait(&mine->B[b][w][0], fz.wait_b);
+    sc->gBM[slot][w][1] = tag_wait(&mine->B[b][w][1], fz.wait_b);
+  }
+}
+// one thread: complete gA[*] from the peers' phase A of this iteration
+__device__ __forceinline__ void fused_fill_A(const Fused& fz, Scal* sc) {
+  if (!fz.on) return;
+  const FusedBox* mine = fz.box[sc->rank];
+  const int b = (int)(fz.stamp & 3ull);
+  for (int w = 0; w < sc->world; ++w)
+    if (w != sc->rank) sc->gA[w] = tag_wait(&mine->A[b][w], fz.stamp);
+}
+// Two-level wait.  A system-scope acquire in every CTA of a 2000-CTA launch costs ~60 us per
+// launch on a busy SM (it drains the SM's outstanding memory traffic), so only the leader --
+// the first CTA of the launch -- talks to the peers' stamps; it completes the local slot arrays
+// and publishes a device-local stamp that every other CTA polls with plain volatile loads
+// (the slots themselves are read with ld.cg afterwards).
+__device__ __forceinline__ void spin_local(const unsigned long long* f, unsigned long long want) {
+  const volatile unsigned long long* vf = f;
+  unsigned long long t0 = 0;
+  for (unsigned spin = 1; *vf < want; ++spin) {
+    if ((spin & 1023u) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fused_sync_B(const Fused& fz, Scal* sc, int slot, bool leader) {
+  if (!fz.on || fz.wait_b == 0) return;
+  if (leader) {
+    fused_fill_B(fz, sc, slot);
+    __threadfence();
+    *reinterpret_cast<volatile unsigned long long*>(&sc->fillB) = fz.wait_b;
+  } else {
+    spin_local(&sc->fillB, fz.wait_b);
+  }
+}
+__device__ __forceinline__ void fused_sync_A(const Fused& fz, Scal* sc, bool leader) {
+  if (!fz.on) return;
+  if (leader) {
+    fused_fill_A(fz, sc);
+    __threadfence();
+    *reinterpret_cast<volatile unsigned long long*>(&sc->fillA) = fz.stamp;
+  } else {
+    spin_local(&sc->fillA, fz.stamp);
+  }
+}
+// one thread (of the last CTA): this rank's scalar(s) of iteration fz.stamp -> every peer
+__device__ __forceinline__ void fused_push_A(const Fused& fz, const Scal* sc, double v) {
+  if (!fz.on) return;
+  const int b = (int)(fz.stamp & 3ull), r = sc->rank;
+  for (int w = 0; w < sc->world; ++w)
+    if (w != r) tag_store(&fz.box[w]->A[b][r], v, fz.stamp);
+}
+__device__ __forceinline__ void fused_push_B(const Fused& fz, const Scal* sc, double v0, double v1) {
+  if (!fz.on) return;
+  const int b = (int)(fz.stamp & 3ull), r = sc->rank;
+  for (int w = 0; w < sc->world; ++w)
+    if (w != r) {
+      tag_store(&fz.box[w]->B[b][r][0], v0, fz.stamp);
+      tag_store(&fz.box[w]->B[b][r][1], v1, fz.stamp);
+    }
+}
 
 template <typename T, int N>
 struct alignas((sizeof(T) * N > 16) ? 16 : sizeof(T) * N) VecT {

@@ -649,13 +649,89 @@ __global__ void k_dir_boundary(Geo g, const uint8_t* __restrict__ codes,
   }
 }
 
+// The same over peer memory (fp32, nx % 4 = 0): s' of the two boundary planes goes straight
+// into the neighbours' halo planes of the s' buffer (peer-mapped stores over NVLink), then the
+// iteration stamp into their boxes -- no local copy (phase A forms these planes itself) and no
+// NCCL call.  lo_dst / hi_dst: the neighbour's halo plane (NULL at the global ends).
+template <int PC>
+__global__ void __launch_bounds__(256)
+k_send_boundary(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ zr,
+                const float* __restrict__ sold, float* __restrict__ lo_dst,
+                float* __restrict__ hi_dst, Scal* __restrict__ sc, int par, Fused fz,
+                unsigned* __restrict__ ticket) {
+  __shared__ int s_stop;
+  __shared__ float s_beta;
+  if (threadIdx.x == 0) {
+    int stop = sc->done;
+    float beta = 0.f;
+    if (!stop) {
+      fused_sync_B(fz, sc, par ^ 1, blockIdx.x == 0);
+      const double rho1 = rho_of(sc, par ^ 1);
+      const double rho2 = rho_of(sc, par);
+      const double rmax = rmax_of(sc, par ^ 1);
+      if (!(rmax == rmax) || rmax <= sc->tol * sc->bmax || rho1 == 0.0) stop = 1;   // phase A stops too
+      else beta = (float)(rho1 / rho2);
+    }
+    s_stop = stop;
+    s_beta = beta;
+  }
+  __syncthreads();
+  if (s_stop) return;
+  const float beta = s_beta;
+  const long long n4 = g.plane / 4;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < 2 * n4;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int which = t >= n4;
+    float* __restrict__ dst = which ? hi_dst : lo_dst;
+    if (!dst) continue;
+    const long long o = (t - which * n4) * 4;
+    const long long idx = (which ? (long long)(g.nz - 1) * g.plane : 0) + o;
+    const float4 a = *reinterpret_cast<const float4*>(zr + idx);
+    const float4 b = *reinterpret_cast<const float4*>(sold + idx);
+    const unsigned cd = *reinterpret_cast<const unsigned*>(codes + idx);
+    float4 r;
+    // the rounding of phase A's dirf: zz = a / diag (one multiply), then fma(beta, s, zz)
+    if (PC == PC_JACOBI) {
+      r.x = __fmaf_rn(beta, b.x, __fmul_rn(a.x, inv_diag<float>(cd & 0xffu)));
+      r.y = __fmaf_rn(beta, b.y, __fmul_rn(a.y, inv_diag<float>((cd >> 8) & 0xffu)));
+      r.z = __fmaf_rn(beta, b.z, __fmul_rn(a.z, inv_diag<float>((cd >> 16) & 0xffu)));
+      r.w = __fmaf_rn(beta, b.w, __fmul_rn(a.w, inv_diag<float>(cd >> 24)));
+    } else {
+      r.x = __fmaf_rn(beta, b.x, a.x); r.y = __fmaf_rn(beta, b.y, a.y);
+      r.z = __fmaf_rn(beta, b.z, a.z); r.w = __fmaf_rn(beta, b.w, a.w);
+    }
+    *reinterpret_cast<float4*>(dst + o) = r;
+  }
+  // ONE system-scope fence per CTA (a membar.sys in every thread stalls the memory pipeline of
+  // the SMs this kernel shares with phase A for tens of microseconds): the barrier orders the
+  // CTA's peer stores before thread 0, whose release is cumulative over them
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1u) {
+      *ticket = 0u;
+      __threadfence_system();
+      const int rank = sc->rank;
+      if (lo_dst) st_release_sys(&fz.box[rank - 1]->hseq[1], fz.stamp);
+      if (hi_dst) st_release_sys(&fz.box[rank + 1]->hseq[0], fz.stamp);
+    }
+  }
+}
+
+// slots of the last phase B of a solve, for the kernels that follow the loop
+__global__ void k_fused_wait_B(Scal* sc, int slot, Fused fz) {
+  if (sc->done) return;
+  if (threadIdx.x == 0) fused_fill_B(fz, sc, slot);
+}
+
 // ---- phase B ---------------------------------------------------------------
 // init != 0: alpha forced to 0 (used once per solve to produce rho_0, max|b|).
 template <typename T, int VEC, int PC>
 __global__ void __launch_bounds__(256)
 k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
          const T* __restrict__ q, const T* __restrict__ z, Scal* __restrict__ sc,
-         double* __restrict__ partials, int par, int init, int nsbuf) {
+         double* __restrict__ partials, int par, int init, int nsbuf, Fused fz) {
   __shared__ double red[32];
   __shared__ double s_alpha;
   __shared__ T lut[8];
@@ -665,6 +741,7 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
   if (tid == 0) {
     double alpha = 0.0;
     if (!init) {
+      fused_sync_A(fz, sc, blockIdx.x == 0);   // z-slabs over peer memory: s.q of the other ranks
       const double rho1 = rho_of(sc, par ^ 1);
       const double sq = sum_slots(sc->gA, sc->world);
       alpha = rho1 / sq;
@@ -727,6 +804,7 @@ k_phaseB(Geo g, const uint8_t* __restrict__ codes, T* __restrict__ r,
       if (!pc_explicit_z(PC)) sc->gBM[par][rank][0] = t;
       sc->gBM[par][rank][1] = nanf ? kNaN : m;
       if (!init) sc->count = sc->count + 1;
+      if (!init && !pc_explicit_z(PC)) fused_push_B(fz, sc, t, nanf ? kNaN : m);
     }
   }
 }

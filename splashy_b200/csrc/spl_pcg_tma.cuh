@@ -88,13 +88,19 @@ k_phaseA_tma(const __grid_constant__ CUtensorMap tm_zr, const __grid_constant__ 
              const __grid_constant__ CUtensorMap tm_snew, const __grid_constant__ CUtensorMap tm_codes,
              Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ zr,
              const float* __restrict__ sold, float* __restrict__ snew, float* __restrict__ q,
-             Scal* __restrict__ sc, double* __restrict__ partials, int par, int zchunk) {
+             Scal* __restrict__ sc, double* __restrict__ partials, int par, int zchunk,
+             int zb0, int zstr, unsigned nbt, Fused fz) {
+  // z-chunk of this CTA = zb0 + blockIdx.z * zstr; nbt = CTAs of the whole phase (a slab runs
+  // its interior chunks while the halo planes travel and the two boundary chunks afterwards:
+  // two launches that share the partials array and the ticket)
   extern __shared__ __align__(1024) unsigned char smem_tma[];
   TmaSmem& sm_ = *reinterpret_cast<TmaSmem*>(smem_tma);
   constexpr int NTHR = 32 * (TILE_Y + 1);
   const int tid = threadIdx.x + threadIdx.y * 32;
   fill_inv_lut<float>(sm_.lut);
   if (tid == 0) {
+    // z-slabs over peer memory: rho, max|r| of the other ranks
+    if (!sc->done) fused_sync_B(fz, sc, par ^ 1, (blockIdx.x | blockIdx.y | blockIdx.z) == 0);
     phaseA_scalars(sc, par, &sm_.stop, &sm_.beta);
     mbar_init(&sm_.bar, NTHR);
 #pragma unroll
@@ -110,10 +116,23 @@ k_phaseA_tma(const __grid_constant__ CUtensorMap tm_zr, const __grid_constant__ 
   const int lane = threadIdx.x, ty = threadIdx.y;
   const int i0 = (blockIdx.x * 32 + lane) * 4;
   const int j0 = blockIdx.y * TILE_Y;
-  const int kb = blockIdx.z * zchunk;
+  // fz.on: one launch for the whole slab, with the two boundary chunks (the only ones that
+  // read a halo plane) dispatched last -- long after the neighbours' planes have arrived
+  const int bz = (fz.halo && !(fz.mode & 4)) ? (int)((blockIdx.z + 1u) % gridDim.z)
+                                             : zb0 + (int)blockIdx.z * zstr;
+  const int kb = bz * zchunk;
   const int ke = min(kb + zchunk, g.nz);
   const int nz = g.nz;
   const long long row = g.nx, plane = g.plane;
+  if (fz.halo) {
+    if (tid == 0) {     // plain polls: the planes are read from L2 (TMA, ld.cg) after the stamp
+      const FusedBox* mine = fz.box[sc->rank];
+      if (kb == 0 && sc->rank > 0) spin_local(&mine->hseq[0], fz.stamp);
+      if (ke == nz && sc->rank < sc->world - 1) spin_local(&mine->hseq[1], fz.stamp);
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async;\n" ::: "memory");   // the planes were written by generic stores
+  }
 
   auto dirf = [&](float a, float o, unsigned code) {
     const float zz = (PC == PC_JACOBI) ? a * lut[lut_index(code)] : a;
@@ -153,7 +172,7 @@ k_phaseA_tma(const __grid_constant__ CUtensorMap tm_zr, const __grid_constant__ 
     if (active) {                                     // plane kb-1: registers
       const long long idm = idx0 - plane;
       if (kb - 1 < 0) {
-        smv = *reinterpret_cast<const float4*>(snew + idm);
+        smv = __ldcg(reinterpret_cast<const float4*>(snew + idm));
       } else {
         smv = dir4(*reinterpret_cast<const float4*>(zr + idm),
                    *reinterpret_cast<const float4*>(sold + idm),
@@ -262,14 +281,17 @@ k_phaseA_tma(const __grid_constant__ CUtensorMap tm_zr, const __grid_constant__ 
   }
 
   const double bs = block_sum(acc, sm_.red);
-  const unsigned nb = num_blocks();
-  if (tid == 0) partials[linear_block()] = bs;
+  const unsigned nb = nbt;
+  if (tid == 0) partials[blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * (unsigned)bz)] = bs;
   if (last_block(&sc->ticketA, nb)) {
     double t = 0.0;
     if (tid < 32 * TILE_Y)
       for (unsigned b = tid; b < nb; b += 32 * TILE_Y) t += __ldcg(partials + b);
     t = block_sum(t, sm_.red);
-    if (tid == 0) sc->gA[sc->rank] = t;
+    if (tid == 0) {
+      sc->gA[sc->rank] = t;
+      fused_push_A(fz, sc, t);
+    }
   }
 }
 

@@ -102,9 +102,14 @@ def main():
     cases = [("vortex_f32", 64, 48, 16 * world, np.float32, 0, False),
              ("vortex_f64", 36, 20, 12 * world, np.float64, 0, False),
              ("vortex_f32_fixed", 64, 48, 16 * world, np.float32, 25, False),
-             ("vortex_f64_uneven", 23, 17, 9 * world + 3, np.float64, 0, True)]
+             ("vortex_f64_uneven", 23, 17, 9 * world + 3, np.float64, 0, True),
+             # 6+ z-chunks per slab: phase A runs as interior + boundary launches around the
+             # side-stream halo exchange (spl_api.cu pcg); 40 iterations cross two x flushes
+             ("vortex_f32_split_fixed", 128, 64, 48 * world, np.float32, 40, False),
+             ("vortex_f32_split", 128, 64, 48 * world, np.float32, 0, False)]
     cases = [c + ("jacobi",) for c in cases]
     cases += [("mg_f32_march_bottom", 128, 64, 32 * world, np.float32, 0, False, "mg"),
+              ("mg_f64_uneven", 24, 20, 32 + 2 * (world - 1), np.float64, 0, True, "mg"),
               ("mg_f32_small", 64, 48, 16 * world, np.float32, 0, False, "mg"),
               ("mg_f64", 36, 20, 12 * world, np.float64, 0, False, "mg")]
     only = os.environ.get("MGPU_ONLY")
