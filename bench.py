@@ -41,6 +41,10 @@ BYTES_PHASE_A = 17     # r 4 + s 4 + code 1 -> s' 4 + q 4                 (DESIG
 BYTES_PHASE_B = 13     # r 4 + q 4 + code 1 -> r 4  (Jacobi)
 BYTES_XFLUSH = 4 * NSBUF + 16   # per launch: NSBUF directions + fp64 x read / write
 BYTES_ITER = BYTES_PHASE_A + BYTES_PHASE_B + BYTES_XFLUSH / NSBUF
+BYTES_ADVECT = 25      # u,v,w 12 + label 1 -> u',v',w' 12                 
+BYTES_RHS = 17         # u,v,w 12 + code 1 -> b 4
+BYTES_GRAD = 33        # p 8 (fp64) + label 1 + u,v,w 12 -> u,v,w 12
+BYTES_CHECK = 21       # u,v,w 12 + p 8 + code 1
 
 
 def parse_args():
@@ -54,22 +58,30 @@ def parse_args():
     ap.add_argument("--precond", default="jacobi", choices=["none", "jacobi", "rbic0", "mg"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tolerance-run", action="store_true")
-    ap.add_argument("--cpu-n", type=int, default=128, help="edge of the CPU sample box")
+    ap.add_argument("--cpu-n", type=int, default=256,
+                    help="edge of the CPU sample box (256^3: 0.7 GB working set, out of cache)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the same slab per GPU; strong: ONE n^3 box over the GPUs (cfg4)")
+    ap.add_argument("--geometry", default="cube", choices=["cube", "cfg5"],
+                    help="per-GPU slab: cube = n^3; cfg5 = 2n x 2n x n/4 (1024 x 1024 x 128)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 slab-vs-one-GPU check")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="N > 1: skip the short cfg4-strong / cfg5 runs")
     return ap.parse_args()
 
 
 def ncu_traffic(kernel: str, n: int):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture
-    (profiles/r1_traffic.json, taken at 512^3); None for any other size."""
-    p = ROOT / "profiles" / "r1_traffic.json"
-    if n != 512 or not p.exists():
+    """DRAM bytes per launch of `kernel` from the committed ncu captures (taken at 512^3);
+    None for any other size."""
+    if n != 512:
         return None
-    try:
-        t = json.loads(p.read_text())
-        key = "k_phaseA_ws" if kernel == "k_phaseA" else kernel
-        return float(t[key]["dram_bytes"])
-    except Exception:
-        return None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = ROOT / "profiles" / name
+        try:
+            return float(json.loads(p.read_text())[kernel]["dram_bytes"])
+        except Exception:
+            continue
+    return None
 
 
 def peaks():
@@ -189,132 +201,236 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------
-def run_cuda(args):
-    import torch
-    import torch.distributed as dist
-    from splashy_b200 import PinnedArray, Solver, nccl_unique_id, scenes
+class Dist:
+    """torch.distributed plumbing: rendezvous, barriers, max / sum over ranks."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
-    torch.cuda.set_device(local)
-    nid = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        box = [nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        nid = box[0]
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
+    def nccl_id(self):
+        from splashy_b200 import nccl_unique_id
+        if self.world == 1:
+            return None
+        box = [nccl_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX)
+
+    def sum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def timed_steps(D, s, dt, warmup, steps, sampler=None):
+    """`steps` device-timed spl_step calls after `warmup` untimed ones; the velocity field is
+    reset (device to device, outside the timers) before each.  Returns per-step averages, the
+    device time being the max over ranks."""
+    for _ in range(warmup):
+        s.restore()
+        s.step(dt)
+    D.barrier()
+    if sampler is not None:
+        sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms = 0.0
+    launches = 0
+    stage = {"ms_advect": 0.0, "ms_rhs": 0.0, "ms_solve": 0.0, "ms_grad": 0.0}
+    info = None
+    for _ in range(steps):
+        s.restore()
+        s.timer_start()
+        info = s.step(dt)
+        dev_ms += s.timer_stop()
+        launches += info["kernel_launches"]
+        for k in stage:
+            stage[k] += info[k] / steps
+    D.barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler is not None else None
+    ms = D.max(dev_ms) / steps
+    stage = {k: D.max(v) for k, v in stage.items()}
+    stage["ms_check"] = max(0.0, ms - sum(stage.values()))
+    return {"ms_per_step": ms, "stage_ms": stage, "launches": launches, "info": info,
+            "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks}
+
+
+def mgpu_parity(D, iters=40):
+    """Slab decomposition against the same box on ONE GPU (both through the C ABI): a
+    128 x 64 x 48N vortex, `iters` fixed Jacobi-PCG iterations -- enough z-chunks per slab for
+    the peer-memory iteration, and two x flushes.  The slab result must be bit-identical."""
+    import torch
+    from splashy_b200 import Solver, scenes
+    world, rank = D.world, D.rank
+    nx, ny, nz = 128, 64, 48
+    nzg = nz * world
+    whole = scenes.vortex(nx, ny, nzg, dtype=np.float32)
+    part = scenes.slab_of(whole, rank * nz, nz)
+    with Solver(nx, ny, nz, dtype=np.float32, h=whole["h"], rho=whole["rho"], device=D.local,
+                rank=rank, world=world, nz_global=nzg, z0=rank * nz, nccl_id=D.nccl_id()) as s:
+        s.upload(part["labels"], part["U"], part["V"], part["W"])
+        s.set_fixed_iters(iters)
+        s.step(whole["dt"])
+        got = s.download()
+    mine = torch.from_numpy(np.stack([got[k] for k in "UVWP"])).cuda()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    D.dist.all_gather(parts, mine)
+    res = None
+    if rank == 0:
+        slab = torch.cat(parts, dim=1).cpu().numpy()
+        with Solver(nx, ny, nzg, dtype=np.float32, h=whole["h"], rho=whole["rho"],
+                    device=D.local) as s1:
+            s1.upload(whole["labels"], whole["U"], whole["V"], whole["W"])
+            s1.set_fixed_iters(iters)
+            s1.step(whole["dt"])
+            one = s1.download()
+        vs = max(float(np.abs(one[k]).max()) for k in "UVW")
+        verr = max(float(np.abs(slab[i] - one[k]).max()) for i, k in enumerate("UVW")) / vs
+        perr = float(np.abs(slab[3] - one["P"]).max() / max(1e-30, np.abs(one["P"]).max()))
+        res = {"ok": bool(verr == 0.0 and perr == 0.0), "vel_err": verr, "p_err": perr,
+               "case": f"vortex {nx}x{ny}x{nzg} over {world} slabs vs one GPU, {iters} fixed "
+                       f"Jacobi-PCG iterations, fp32", "bit_identical": bool(verr == 0.0 and perr == 0.0)}
+    D.barrier()
+    return res
+
+
+def run_cuda(args):
+    from splashy_b200 import PinnedArray, Solver, scenes
+
+    D = Dist(args)
+    world, rank, local = D.world, D.rank, D.local
+    parity = mgpu_parity(D) if world > 1 and not args.no_parity else None
+
+    # ---- workload geometry ----------------------------------------------------------------
     n = args.n
-    nzg = n * world
-    sc = scenes.vortex(n, n, n, z0=rank * n, nz_global=nzg, dtype=np.float32)
-    dt = sc["dt"]
-    h_, rho_ = sc["h"], sc["rho"]
-    cells_local = n ** 3
+    if args.scaling == "strong":          # cfg4: ONE n^3 box cut into `world` z-slabs
+        if n % world:
+            raise SystemExit(f"--scaling strong needs n % gpus == 0 ({n} % {world})")
+        nx, ny, nz = n, n, n // world
+        label = f"vortex_{n} (cfg4): one {n}^3 box over {world} z-slab(s) of {nz} planes"
+    elif args.geometry == "cfg5":         # cfg5: 1024 x 1024 x 128 per GPU -> 1024^3 on 8 GPUs
+        nx, ny, nz = 2 * n, 2 * n, n // 4
+        label = f"weak_1024 (cfg5): {nx}x{ny}x{nz} cells per GPU (global {nx}x{ny}x{nz * world})"
+    else:                                 # cfg4 at N = 1; the same slab per GPU as N grows
+        nx, ny, nz = n, n, n
+        label = f"vortex_512: {nx}x{ny}x{nz} cells per GPU (global {nx}x{ny}x{nz * world})"
+    nzg = nz * world
+    sc = scenes.vortex(nx, ny, nz, z0=rank * nz, nz_global=nzg, dtype=np.float32)
+    dt, h_, rho_ = sc["dt"], sc["h"], sc["rho"]
+    cells_local = nx * ny * nz
     cells = cells_local * world
+    shape = (nz, ny, nx)
 
-    s = Solver(n, n, n, dtype=np.float32, h=sc["h"], rho=sc["rho"], precond=args.precond,
-               tol=1e-6, max_iters=20000, device=local, rank=rank, world=world,
-               nz_global=nzg, z0=rank * n, nccl_id=nid)
+    def make(precond, tol=1e-6, max_iters=20000):
+        return Solver(nx, ny, nz, dtype=np.float32, h=h_, rho=rho_, precond=precond, tol=tol,
+                      max_iters=max_iters, device=local, rank=rank, world=world, nz_global=nzg,
+                      z0=rank * nz, nccl_id=D.nccl_id())
+
+    s = make(args.precond)
     # pinned host buffers (the e2e leg copies from / to these every step)
-    hin = {k: PinnedArray((n, n, n), np.float32) for k in "UVW"}
-    hlab = PinnedArray((n, n, n), np.uint8)
-    hout = {k: PinnedArray((n, n, n), np.float32) for k in "UVWP"}
+    hin = {k: PinnedArray(shape, np.float32) for k in "UVW"}
+    hlab = PinnedArray(shape, np.uint8)
+    hout = {k: PinnedArray(shape, np.float32) for k in "UVWP"}
     for k in "UVW":
         hin[k].array[...] = sc[k]
     hlab.array[...] = sc["labels"]
     del sc
     ptr = lambda a: C.c_void_p(a.array.ctypes.data)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     s.upload_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
     s.snapshot()
     s.set_fixed_iters(args.pcg_iters)
 
     # ---- device-resident leg ("value") ---------------------------------------------
-    launches = 0
-    for _ in range(args.warmup):
-        s.restore()
-        s.step(dt)
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    wall0 = time.perf_counter()
-    dev_ms = 0.0
-    solve_ms = 0.0
-    stage = {"ms_advect": 0.0, "ms_rhs": 0.0, "ms_solve": 0.0, "ms_grad": 0.0}
-    for _ in range(args.steps):
-        s.restore()                      # device-to-device reset, outside the timers
-        s.timer_start()
-        info = s.step(dt)
-        dev_ms += s.timer_stop()
-        launches += info["kernel_launches"]
-        solve_ms += info["ms_solve"]
-        for k in stage:
-            stage[k] += info[k] / args.steps
-    barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
-    dev_ms = max_over_ranks(dev_ms)
-    solve_ms = max_over_ranks(solve_ms)
-    ms_per_step = dev_ms / args.steps
+    main = timed_steps(D, s, dt, args.warmup, args.steps, ClockSampler(local) if rank == 0 else None)
+    ms_per_step = main["ms_per_step"]
+    stage = main["stage_ms"]
     value = cells / (ms_per_step * 1e-3)
-    iters_per_s = args.pcg_iters / (solve_ms / args.steps * 1e-3)
-    last_info = info
+    iters_per_s = args.pcg_iters / (stage["ms_solve"] * 1e-3)
+    last_info = main["info"]
 
     # ---- end-to-end leg: host buffers in, host buffers out -------------------------------
-    h2d = n ** 3 * (3 * 4 + 1)
-    d2h = n ** 3 * 4 * 4
-    for _ in range(1):
-        s.upload_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
-        s.step(dt)
-        s.download_ptrs(ptr(hout["U"]), ptr(hout["V"]), ptr(hout["W"]), ptr(hout["P"]))
-    barrier()
+    h2d = cells_local * (3 * 4 + 1)
+    d2h = cells_local * 4 * 4
+    s.upload_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
+    s.step(dt)
+    s.download_ptrs(ptr(hout["U"]), ptr(hout["V"]), ptr(hout["W"]), ptr(hout["P"]))
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         s.upload_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
         s.step(dt)
         s.download_ptrs(ptr(hout["U"]), ptr(hout["V"]), ptr(hout["W"]), ptr(hout["P"]))
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    D.barrier()
+    e2e_s = D.max(time.perf_counter() - t0) / args.steps
     e2e_value = cells / e2e_s
-    checksum = float(hout["P"].array[n // 2, n // 2, ::64].astype(np.float64).sum())
+    checksum = float(hout["P"].array[nz // 2, ny // 2, ::64].astype(np.float64).sum())
 
     # ---- per-kernel roofline: CUDA events around every PCG launch -------------------------
     s.restore()
     ms_a, ms_b, ms_x = s.profile_pcg(dt, 32)
-    ms_a, ms_b, ms_x = max_over_ranks(ms_a), max_over_ranks(ms_b), max_over_ranks(ms_x)
+    ms_a, ms_b, ms_x = D.max(ms_a), D.max(ms_b), D.max(ms_x)
     peak, peak_src = peaks()
-    gbs_a = cells_local * BYTES_PHASE_A / (ms_a * 1e-3) / 1e9
-    gbs_b = cells_local * BYTES_PHASE_B / (ms_b * 1e-3) / 1e9
-    gbs_x = cells_local * BYTES_XFLUSH / (ms_x * 1e-3) / 1e9 if ms_x > 0 else 0.0
-    dom = "k_phaseB" if ms_b >= ms_a else "k_phaseA"
+    gbs = lambda bytes_per_cell, ms: cells_local * bytes_per_cell / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    gbs_a, gbs_b, gbs_x = gbs(BYTES_PHASE_A, ms_a), gbs(BYTES_PHASE_B, ms_b), gbs(BYTES_XFLUSH, ms_x)
+    dom = "k_phaseB" if ms_b >= ms_a else "k_phaseA_tma"
     dom_gbs = gbs_b if dom == "k_phaseB" else gbs_a
-    step_bytes = cells_local * (75 + args.pcg_iters * BYTES_ITER)
-    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+    step_bpc = BYTES_ADVECT + BYTES_RHS + BYTES_GRAD + BYTES_CHECK + args.pcg_iters * BYTES_ITER
+    step_gbs = gbs(step_bpc, ms_per_step)
+    nonpcg_ms = stage["ms_advect"] + stage["ms_rhs"] + stage["ms_grad"]
+    kernels = {
+        "k_phaseA_tma": {"ms": ms_a, "bytes_per_cell": BYTES_PHASE_A, "GBps": gbs_a, "frac": gbs_a / peak},
+        "k_phaseB": {"ms": ms_b, "bytes_per_cell": BYTES_PHASE_B, "GBps": gbs_b, "frac": gbs_b / peak},
+        "k_xflush": {"ms": ms_x, "bytes_per_cell": BYTES_XFLUSH, "every_iters": NSBUF,
+                     "GBps": gbs_x, "frac": gbs_x / peak},
+        # stages of the step outside the solve, from spl_info's CUDA events (sustained clocks:
+        # they run inside the long step)
+        "advect (k_advect_tma + k_advect_rest)": {
+            "ms": stage["ms_advect"], "bytes_per_cell": BYTES_ADVECT,
+            "GBps": gbs(BYTES_ADVECT, stage["ms_advect"]),
+            "frac": gbs(BYTES_ADVECT, stage["ms_advect"]) / peak,
+            "bound": "shared-memory gather pipe (114 LDS.32 / cell), not HBM"},
+        "rhs (k_div_rhs4)": {"ms": stage["ms_rhs"], "bytes_per_cell": BYTES_RHS,
+                             "GBps": gbs(BYTES_RHS, stage["ms_rhs"]),
+                             "frac": gbs(BYTES_RHS, stage["ms_rhs"]) / peak},
+        "grad (k_grad_sub4)": {"ms": stage["ms_grad"], "bytes_per_cell": BYTES_GRAD,
+                               "GBps": gbs(BYTES_GRAD, stage["ms_grad"]),
+                               "frac": gbs(BYTES_GRAD, stage["ms_grad"]) / peak},
+        "check (k_check4)": {"ms": stage["ms_check"], "bytes_per_cell": BYTES_CHECK,
+                             "GBps": gbs(BYTES_CHECK, stage["ms_check"]),
+                             "frac": gbs(BYTES_CHECK, stage["ms_check"]) / peak},
+        "non_pcg (advect + rhs + grad)": {
+            "ms": nonpcg_ms, "bytes_per_cell": BYTES_ADVECT + BYTES_RHS + BYTES_GRAD,
+            "GBps": gbs(BYTES_ADVECT + BYTES_RHS + BYTES_GRAD, nonpcg_ms),
+            "frac": gbs(BYTES_ADVECT + BYTES_RHS + BYTES_GRAD, nonpcg_ms) / peak},
+    }
 
     # ---- one run-to-tolerance step (iteration count, SURVEY 8d cfg4) ------------------------
     tol_run = None
@@ -327,44 +443,37 @@ def run_cuda(args):
             ti = dict(s.last_info)
             ti["error"] = str(e)
         tol_run = {"tol": 1e-6, "precond": args.precond, "iters": ti["iters"], "converged": ti["converged"],
-                   "ms_step": max_over_ranks(ti["ms_total"]), "r_inf": ti["r_inf"],
+                   "ms_step": D.max(ti["ms_total"]), "r_inf": ti["r_inf"],
                    "b_inf": ti["b_inf"], "max_abs_div": ti["max_abs_div"]}
         tol_run["cell_updates_per_s"] = cells / (tol_run["ms_step"] * 1e-3)
         if "error" in ti:
             tol_run["error"] = ti["error"]
+    s.close()
+    s = None
 
-    # ---- the same step with the multigrid preconditioner, to tolerance (1 GPU) ---------------
+    # ---- the same step with the multigrid preconditioner, to tolerance ------------------------
     tol_mg = None
     if not args.no_tolerance_run and args.precond != "mg":
-        s.close()
-        s = None
-        nid2 = None
-        if world > 1:
-            box = [nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
-            nid2 = box[0]
-        smg = Solver(n, n, n, dtype=np.float32, h=h_, rho=rho_, precond="mg", tol=1e-6,
-                     max_iters=2000, device=local, rank=rank, world=world, nz_global=nzg,
-                     z0=rank * n, nccl_id=nid2)
+        smg = make("mg", max_iters=2000)
         smg.upload_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
         smg.snapshot()
         best = None
         for _ in range(3):
             smg.restore()
-            barrier()
+            D.barrier()
             smg.timer_start()
             ti = smg.step(dt)
-            ms = max_over_ranks(smg.timer_stop())
+            ms = D.max(smg.timer_stop())
             if best is None or ms < best[0]:
                 best = (ms, ti)
         ms, ti = best
         # the same without the refinement restart (recursive residual only)
         smg.set_refinement(0)
         smg.restore()
-        barrier()
+        D.barrier()
         smg.timer_start()
         t0 = smg.step(dt)
-        ms0 = max_over_ranks(smg.timer_stop())
+        ms0 = D.max(smg.timer_stop())
         tol_mg = {"tol": 1e-6, "precond": "mg", "iters": ti["iters"], "converged": ti["converged"],
                   "refinement_rounds": 1,
                   "without_refinement": {"iters": t0["iters"], "ms_step": ms0,
@@ -373,58 +482,87 @@ def run_cuda(args):
                   "b_inf": ti["b_inf"], "max_abs_div": ti["max_abs_div"],
                   "cell_updates_per_s": cells / (ms * 1e-3), "best_of": 3}
         smg.close()
+    for a in list(hin.values()) + list(hout.values()) + [hlab]:
+        a.free()
+
+    # ---- N > 1: the other two named configurations, short runs, in the same record ---------------
+    extra = {}
+    if world > 1 and not args.no_extra_configs and args.scaling == "weak" and args.geometry == "cube":
+        def short_run(gx, gy, gz_local, name):
+            scx = scenes.vortex(gx, gy, gz_local, z0=rank * gz_local, nz_global=gz_local * world,
+                                dtype=np.float32)
+            sx = Solver(gx, gy, gz_local, dtype=np.float32, h=scx["h"], rho=scx["rho"],
+                        precond=args.precond, device=local, rank=rank, world=world,
+                        nz_global=gz_local * world, z0=rank * gz_local, nccl_id=D.nccl_id())
+            sx.upload(scx["labels"], scx["U"], scx["V"], scx["W"])
+            sx.snapshot()
+            sx.set_fixed_iters(args.pcg_iters)
+            r = timed_steps(D, sx, scx["dt"], 2, 2)
+            sx.close()
+            tot = gx * gy * gz_local * world
+            return {"workload": name, "ms_per_step": r["ms_per_step"],
+                    "value": tot / (r["ms_per_step"] * 1e-3), "unit": UNIT,
+                    "pcg_iters_per_s": args.pcg_iters / (r["stage_ms"]["ms_solve"] * 1e-3),
+                    "stage_ms": r["stage_ms"], "steps": 2, "warmup": 2}
+        if n % world == 0 and n // world >= 16:
+            extra["strong_cfg4"] = short_run(
+                n, n, n // world, f"cfg4 strong scaling: one {n}^3 box over {world} z-slabs of "
+                                  f"{n // world} planes; compare with the N = 1 line of this bench")
+            extra["strong_cfg4"]["scaling"] = "strong"
+        extra["weak_cfg5"] = short_run(
+            2 * n, 2 * n, n // 4, f"cfg5 geometry: {2 * n}x{2 * n}x{n // 4} cells per GPU "
+                                  f"(global {2 * n}x{2 * n}x{n // 4 * world}), "
+                                  f"{4 * (2 * n) ** 2 // 2 ** 20} MiB halo planes")
+        extra["weak_cfg5"]["scaling"] = "weak"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_sample(args.cpu_n, args.pcg_iters)
 
-    launches_total = int(sum_over_ranks(float(launches)))
+    launches_total = int(D.sum(float(main["launches"])))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"vortex_512: {n}x{n}x{n} cells per GPU (global {n}x{n}x{nzg}), "
-                                   f"z-slabs, CFL 2, fp32 fields / fp64 dots",
+            "config": {"workload": f"{label}, z-slabs, CFL 2, fp32 fields / fp64 dots",
                        "step": "advect + rhs + PCG + gradient + check",
                        "pcg_iters": args.pcg_iters, "precond": args.precond,
                        "l2": "inputs (3 x 512 MiB fields per GPU) exceed the 126 MB L2; no flush",
-                       "parallelism": f"z-slab x{world}, NCCL halo + allgather"},
+                       "parallelism": f"z-slab x{world}; PCG iteration over peer memory (NVLink "
+                                      f"stores of halo planes and CG scalars), NCCL for the rest"},
             "pcg_iters_per_s": iters_per_s,
             "stage_ms": stage,
-            "wall_ms_per_step": wall / args.steps * 1e3,
+            "wall_ms_per_step": main["wall_ms_per_step"],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_s * 1e3,
                     "result_checksum": checksum},
             "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak,
                          "unit": "GB/s", "frac": dom_gbs / peak,
-                         "traffic": ncu_traffic(dom, n),
+                         "traffic": ncu_traffic(dom, n if (nx, ny, nz) == (512, 512, 512) else 0),
                          "algorithmic_bytes": cells_local * (BYTES_PHASE_B if dom == "k_phaseB"
                                                              else BYTES_PHASE_A),
                          "peak_source": peak_src,
-                         "kernels": {"k_phaseA": {"ms": ms_a, "bytes_per_cell": BYTES_PHASE_A,
-                                                  "GBps": gbs_a, "frac": gbs_a / peak},
-                                     "k_phaseB": {"ms": ms_b, "bytes_per_cell": BYTES_PHASE_B,
-                                                  "GBps": gbs_b, "frac": gbs_b / peak},
-                                     "k_xflush": {"ms": ms_x, "bytes_per_cell": BYTES_XFLUSH,
-                                                  "every_iters": NSBUF, "GBps": gbs_x,
-                                                  "frac": gbs_x / peak}},
-                         "whole_step": {"bytes_per_cell": 75 + args.pcg_iters * BYTES_ITER,
+                         "byte_model": "DESIGN.md section 4 (this build's arrays: 35 B/cell/iteration; "
+                                       "SURVEY 8d's 45 B model would read 1.29x higher)",
+                         "kernels": kernels,
+                         "whole_step": {"bytes_per_cell": step_bpc,
                                         "GBps": step_gbs, "frac": step_gbs / peak}},
-            "clocks": clocks,
+            "clocks": main["clocks"],
             "to_tolerance": tol_run,
             "to_tolerance_mg": tol_mg,
             "check": {"max_abs_div": last_info["max_abs_div"], "nonfinite": last_info["nonfinite"]},
         }
+        if parity is not None:
+            line["mgpu_parity"] = parity
+        if extra:
+            line["other_configs"] = extra
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    if s is not None:
-        s.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 def main():

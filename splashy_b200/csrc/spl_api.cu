@@ -1066,7 +1066,14 @@ struct Impl {
     const int gridB = grid_for(c, g.ncell / VEC);
     const int tx = (g.nx + 32 * VEC - 1) / (32 * VEC);
     const int ty = (g.ny + TILE_Y - 1) / TILE_Y;
-    const int zc = phaseA_zchunk(c, tx * ty);
+    int zc = phaseA_zchunk(c, tx * ty);
+    // z-slabs over peer memory: at least four z-chunks, so that the two boundary chunks (which
+    // wait for the neighbours' planes) are the second half of the launch at most
+    if (c->d.world > 1 && c->fused_ok && !pc_explicit_z(PC) && phaseA_splits(c) &&
+        c->zchunk_override <= 0 && (g.nz + zc - 1) / zc < 4) {
+      zc = g.nz / 4;
+      if (zc < 8) zc = 8;
+    }
     const dim3 gridA(tx, ty, (g.nz + zc - 1) / zc);
     const dim3 blockA(32, TILE_Y);
     const T* zr = pc_explicit_z(PC) ? P(c->z) : P(c->r);
