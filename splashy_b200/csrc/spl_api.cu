@@ -255,6 +255,7 @@ struct spl_ctx {
   int mgt_attr_set = 0;
   bool no_ws = false;          // SPL_NO_WS=1: ring kernel without the halo warp (k_phaseA_ring)
   bool no_quad = false;        // SPL_NO_QUAD=1: one-cell-per-thread div / grad / check kernels
+  bool no_gc_fuse = false;     // SPL_NO_GC_FUSE=1: k_grad_sub4 + k_check4 instead of k_grad_check4
   // cell-centred scalar fields advected with the velocity (spl_set_scalars); scal2 = target
   std::vector<char*> scal;
   char* scal2 = nullptr;
@@ -1019,6 +1020,15 @@ struct Impl {
   static int precondition(spl_ctx* c, int par, bool fuse_r = false) {
     if (c->d.precond == SPL_PC_MG) return vcycle(c, par, fuse_r);
     const Geo& g = c->g;
+    if constexpr (std::is_same<T, float>::value) {
+      if (g.nx % 4 == 0 && !c->no_quad) {     // quad kernels: same z, 30 B / cell
+        const int gq = grid_for(c, g.ncell / 4);
+        LAUNCH(c, k_rb_black4, gq, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc);
+        LAUNCH(c, k_rb_red4, gq, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc,
+               c->partials, par);
+        return SPL_OK;
+      }
+    }
     const int grid = grid_for(c, g.ncell);
     LAUNCH(c, (k_rb_sweep<T, 1>), grid, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc,
            c->partials, par);
@@ -1256,6 +1266,35 @@ struct Impl {
            P(c->v), P(c->w), kappa);
     CU(cudaGetLastError());
     return SPL_OK;
+  }
+
+  // Pressure.apply + the checks as one marching pass (k_grad_check4): fp32 quads only
+  static bool grad_check_ok(const spl_ctx* c) {
+    return std::is_same<T, float>::value && c->g.nx % 4 == 0 && !c->no_quad && !c->no_gc_fuse;
+  }
+  static int grad_check(spl_ctx* c, double dt) {
+    if constexpr (std::is_same<T, float>::value) {
+      const Geo& g = c->g;
+      // halos: p of the neighbouring slabs' boundary planes, and the velocity below the slab
+      // (the incoming z face of plane 0 is recomputed from the OLD w of plane -1)
+      int rc = exchange_halo(c, c->p, 8, ncclDouble, 1);
+      if (rc) return rc;
+      if ((rc = exchange_velocity(c, 1))) return rc;
+      const double kappa = dt / (c->d.h * c->d.rho);
+      const int tx = (g.nx + 127) / 128, ty = (g.ny + GC_TY - 1) / GC_TY;
+      const int zc = phaseA_zchunk(c, tx * ty);
+      const dim3 grid(tx, ty, (g.nz + zc - 1) / zc);
+      k_grad_check4<<<grid, dim3(32, GC_TY), 0, c->stream>>>(
+          g, c->media, c->codes, reinterpret_cast<const double*>(c->p), P(c->u), P(c->v), P(c->w),
+          P(c->u2), P(c->v2), P(c->w2), kappa, c->sc, c->partials, zc);
+      c->launches++;
+      CU(cudaGetLastError());
+      std::swap(c->u, c->u2);
+      std::swap(c->v, c->v2);
+      std::swap(c->w, c->w2);
+      return gather_slots(c, c->sc->gD, 1);
+    }
+    return SPL_E_BADARG;
   }
 
   static int check(spl_ctx* c) {
@@ -1524,6 +1563,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   if (const char* e = getenv("SPL_TMA_L2")) c->tma_l2 = atoi(e) & 3;
   c->tmaps.reserve(256);
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
+  if (const char* e = getenv("SPL_NO_GC_FUSE")) c->no_gc_fuse = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
   if (const char* e = getenv("SPL_ADV_TMA")) c->adv_tma = atoi(e) != 0;
   if (const char* e = getenv("SPL_ADV_FUSE")) c->adv_fuse = atoi(e) != 0;
@@ -2023,9 +2063,14 @@ static int project_impl(spl_ctx* c, double dt, spl_info* info, bool with_advect)
     c->iters_base += it0;
   }
   CU(cudaEventRecord(c->ev[3], c->stream));
-  if ((rc = DISPATCH(c, Impl<float>::grad(c, dt), Impl<double>::grad(c, dt)))) return rc;
-  CU(cudaEventRecord(c->ev[4], c->stream));
-  if ((rc = DISPATCH(c, Impl<float>::check(c), Impl<double>::check(c)))) return rc;
+  if (c->d.dtype == SPL_F32 && Impl<float>::grad_check_ok(c)) {
+    if ((rc = Impl<float>::grad_check(c, dt))) return rc;       // one pass, 34 B / cell
+    CU(cudaEventRecord(c->ev[4], c->stream));
+  } else {
+    if ((rc = DISPATCH(c, Impl<float>::grad(c, dt), Impl<double>::grad(c, dt)))) return rc;
+    CU(cudaEventRecord(c->ev[4], c->stream));
+    if ((rc = DISPATCH(c, Impl<float>::check(c), Impl<double>::check(c)))) return rc;
+  }
   CU(cudaEventRecord(c->ev[5], c->stream));
   spl_info local;
   memset(&local, 0, sizeof local);

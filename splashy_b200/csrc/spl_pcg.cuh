@@ -940,6 +940,160 @@ k_rb_sweep(Geo g, const uint8_t* __restrict__ codes, const T* __restrict__ r,
   }
 }
 
+// ---- the two half sweeps, four x cells per thread (fp32, nx % 4 = 0) -----------------
+// Same expressions, neighbour order and guards as k_rb_sweep, cell by cell, so z is bit
+// for bit the one-cell kernel's; what changes is the data movement: a thread owns an
+// aligned quad (two red and two black cells, colours alternate from the parity of
+// j + k + z0), every array is read with 128-bit loads -- own row, the +-y rows and the
+// +-z planes -- plus one scalar either side for the x neighbours outside the quad, and z is
+// written as whole quads.  BLACK pass: z_B on black cells, 0 on red ones (13 B / cell);
+// RED pass: z_R from the black z around it, black values carried through, r.z reduced
+// over all four cells (17 B / cell).  No per-cell div / mod, no idle half-warps.
+struct RbQuad {
+  long long idx;
+  int k;
+  unsigned p0;            // colour of cell 0 of the quad (1 = black)
+  unsigned c[4];          // stencil codes
+};
+__device__ __forceinline__ RbQuad rb_quad(const Geo& g, long long q, int qx,
+                                          const uint8_t* __restrict__ codes) {
+  RbQuad r;
+  r.idx = q << 2;
+  const long long t = q / qx;
+  const int j = (int)(t % g.ny);
+  r.k = (int)(t / g.ny);
+  r.p0 = (unsigned)(j + r.k + g.z0) & 1u;
+  const unsigned c4 = *reinterpret_cast<const unsigned*>(codes + r.idx);
+  r.c[0] = c4 & 0xffu; r.c[1] = (c4 >> 8) & 0xffu; r.c[2] = (c4 >> 16) & 0xffu; r.c[3] = c4 >> 24;
+  return r;
+}
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p, long long idx) {
+  return *reinterpret_cast<const float4*>(p + idx);
+}
+
+__global__ void __launch_bounds__(256)
+k_rb_black4(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ r,
+            const float* __restrict__ einv, float* __restrict__ z, Scal* __restrict__ sc) {
+  if (sc->done) return;
+  const long long nq = g.ncell >> 2;
+  const int qx = g.nx >> 2;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq;
+       q += (long long)gridDim.x * blockDim.x) {
+    const RbQuad Q = rb_quad(g, q, qx, codes);
+    const long long idx = Q.idx;
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    const unsigned any = (Q.c[0] | Q.c[1] | Q.c[2] | Q.c[3]) & B_FLUID;
+    if (any) {
+      const float4 r4 = ld4(r, idx), e4 = ld4(einv, idx);
+      const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+      // r einv of the red neighbours; a row / plane is fetched only if some cell of the
+      // quad has that neighbour (the guards of k_rb_sweep)
+      const unsigned all = Q.c[0] | Q.c[1] | Q.c[2] | Q.c[3];
+      const bool zm = Q.k > 0, zp = Q.k < g.nz - 1;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 rym = z4, eym = z4, ryp = z4, eyp = z4, rzm = z4, ezm = z4, rzp = z4, ezp = z4;
+      if (all & B_YM) { rym = ld4(r, idx - g.nx); eym = ld4(einv, idx - g.nx); }
+      if (all & B_YP) { ryp = ld4(r, idx + g.nx); eyp = ld4(einv, idx + g.nx); }
+      if ((all & B_ZM) && zm) { rzm = ld4(r, idx - g.plane); ezm = ld4(einv, idx - g.plane); }
+      if ((all & B_ZP) && zp) { rzp = ld4(r, idx + g.plane); ezp = ld4(einv, idx + g.plane); }
+      const float* a_rym = reinterpret_cast<const float*>(&rym);
+      const float* a_eym = reinterpret_cast<const float*>(&eym);
+      const float* a_ryp = reinterpret_cast<const float*>(&ryp);
+      const float* a_eyp = reinterpret_cast<const float*>(&eyp);
+      const float* a_rzm = reinterpret_cast<const float*>(&rzm);
+      const float* a_ezm = reinterpret_cast<const float*>(&ezm);
+      const float* a_rzp = reinterpret_cast<const float*>(&rzp);
+      const float* a_ezp = reinterpret_cast<const float*>(&ezp);
+      float rx[6], ex[6];                           // r, einv at i-1 .. i+4
+      rx[0] = ex[0] = rx[5] = ex[5] = 0.f;
+      if (Q.p0 == 1u && (Q.c[0] & B_XM)) { rx[0] = r[idx - 1]; ex[0] = einv[idx - 1]; }
+      if (Q.p0 == 0u && (Q.c[3] & B_XP)) { rx[5] = r[idx + 4]; ex[5] = einv[idx + 4]; }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { rx[e + 1] = rr[e]; ex[e + 1] = ee[e]; }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned c = Q.c[e];
+        if ((((unsigned)e ^ Q.p0) & 1u) && (c & B_FLUID)) {   // black Fluid cell
+          // one fused multiply-add per neighbour: what `sum += r * einv` compiles to in
+          // k_rb_sweep
+          float sum = 0.f;
+          if (c & B_XM) sum = fmaf(rx[e], ex[e], sum);
+          if (c & B_XP) sum = fmaf(rx[e + 2], ex[e + 2], sum);
+          if (c & B_YM) sum = fmaf(a_rym[e], a_eym[e], sum);
+          if (c & B_YP) sum = fmaf(a_ryp[e], a_eyp[e], sum);
+          if ((c & B_ZM) && zm) sum = fmaf(a_rzm[e], a_ezm[e], sum);
+          if ((c & B_ZP) && zp) sum = fmaf(a_rzp[e], a_ezp[e], sum);
+          zz[e] = (rr[e] + sum) * ee[e];
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(z + idx) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_rb_red4(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ r,
+          const float* __restrict__ einv, float* __restrict__ z, Scal* __restrict__ sc,
+          double* __restrict__ partials, int par_slot) {
+  __shared__ double red[32];
+  if (sc->done) return;
+  double acc = 0.0;
+  const long long nq = g.ncell >> 2;
+  const int qx = g.nx >> 2;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq;
+       q += (long long)gridDim.x * blockDim.x) {
+    const RbQuad Q = rb_quad(g, q, qx, codes);
+    const long long idx = Q.idx;
+    const unsigned any = (Q.c[0] | Q.c[1] | Q.c[2] | Q.c[3]) & B_FLUID;
+    if (!any) continue;            // z = 0 there already (black pass), r.z terms are 0
+    const float4 r4 = ld4(r, idx), e4 = ld4(einv, idx), z4 = ld4(z, idx);
+    const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+    float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+    const unsigned all = Q.c[0] | Q.c[1] | Q.c[2] | Q.c[3];
+    const bool zm = Q.k > 0, zp = Q.k < g.nz - 1;
+    float4 aym = make_float4(0.f, 0.f, 0.f, 0.f), ayp = aym, azm = aym, azp = aym;
+    if (all & B_YM) aym = ld4(z, idx - g.nx);
+    if (all & B_YP) ayp = ld4(z, idx + g.nx);
+    if ((all & B_ZM) && zm) azm = ld4(z, idx - g.plane);
+    if ((all & B_ZP) && zp) azp = ld4(z, idx + g.plane);
+    const float ym[4] = {aym.x, aym.y, aym.z, aym.w}, yp[4] = {ayp.x, ayp.y, ayp.z, ayp.w};
+    const float zmv[4] = {azm.x, azm.y, azm.z, azm.w}, zpv[4] = {azp.x, azp.y, azp.z, azp.w};
+    float zx[6];                                    // black z at i-1 .. i+4
+    zx[0] = (Q.p0 == 0u && (Q.c[0] & B_XM)) ? z[idx - 1] : 0.f;
+    zx[5] = (Q.p0 == 1u && (Q.c[3] & B_XP)) ? z[idx + 4] : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) zx[e + 1] = zz[e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned c = Q.c[e];
+      if (!(((unsigned)e ^ Q.p0) & 1u)) {           // red cell
+        float v = 0.f;
+        if (c & B_FLUID) {
+          float sum = 0.f;
+          if (c & B_XM) sum += zx[e];
+          if (c & B_XP) sum += zx[e + 2];
+          if (c & B_YM) sum += ym[e];
+          if (c & B_YP) sum += yp[e];
+          if ((c & B_ZM) && zm) sum += zmv[e];
+          if ((c & B_ZP) && zp) sum += zpv[e];
+          v = (rr[e] + sum) * ee[e];
+        }
+        zz[e] = v;
+      }
+      acc += (double)rr[e] * (double)zz[e];
+    }
+    *reinterpret_cast<float4*>(z + idx) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+  }
+  const double bs = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+  if (last_block(&sc->ticketC, gridDim.x)) {
+    double t = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(partials + b);
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) sc->gBM[par_slot][sc->rank][0] = t;
+  }
+}
+
 // ---- deferred pressure update ----------------------------------------------------
 // Iteration it leaves its search direction in ring buffer it % m and its step
 // length in alpha_hist[it % m]; this kernel adds every pending term

@@ -322,6 +322,256 @@ k_check4(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ u,
   }
 }
 
+// ---- gradient subtraction + validators in one pass (fp32, nx % 4 = 0) -------------------
+// Pressure.apply followed by the checks (Pressure.fs:96-149): the same arithmetic, cell by
+// cell, as k_grad_sub4 then k_check4, with every array pulled from HBM once:
+//   labels 1 + codes 1 + p 8 + u, v, w 12 in, 12 out = 34 B / cell   (33 + 21 as two passes)
+// A CTA owns a 128 x GC_TY tile of the x-y plane (a thread = one aligned quad) and marches
+// along z.  The pressure and labels of plane k+1 (the +z neighbours) are this plane's loads
+// and the next plane's own values, carried in registers, and so is the new w of plane k-1
+// (the incoming z face of the divergence).  The +-y neighbours' p and labels go through a
+// double-buffered shared-memory tile (one barrier per plane); the incoming y face v'(j-1) is
+// recomputed from them and the old v of row j-1 (an L1 / L2 hit: the row above loads the same
+// line), the incoming x face u'(i-1) comes from the lane on the left.  Only the tile-edge rows /
+// lanes read their halo from global memory.
+// Out of place (u, v, w -> u2, v2, w2), so a halo is always an OLD value whichever CTA runs first.
+// Packed label logic of grad_face for four cells at once (one label per byte, any byte value):
+// bit 0 of byte e of `ns` = "label e is Air or Fluid" ((label & 0xfe) == 0), of `fl` = "Fluid".
+__device__ __forceinline__ unsigned gc_ns4(unsigned m) {
+  const unsigned t = m & 0xfefefefeu;
+  return (~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u) >> 7;
+}
+struct GcFace {
+  unsigned both, zero;   // bit 8e: face e takes the pressure gradient / the solid velocity 0
+};
+__device__ __forceinline__ GcFace gc_face4(unsigned ns0, unsigned fl0, unsigned ns1, unsigned fl1) {
+  GcFace f;
+  f.both = ns0 & ns1 & (fl0 | fl1);
+  f.zero = (fl0 & ~ns1) | (~ns0 & fl1);
+  return f;
+}
+// p0, p1 are already 0 on non-Fluid cells (sanitised when they enter the shared tile), so the
+// value is grad_face's (double)f - kappa ((fl1 ? p1 : 0) - (fl0 ? p0 : 0)), computed
+// unconditionally and selected by the masks: no branches.
+__device__ __forceinline__ float gc_apply(const GcFace& fm, int e, double p0, double p1, float f,
+                                          double kappa) {
+  const float val = (float)((double)f - kappa * (p1 - p0));
+  const float keep = ((fm.zero >> (8 * e)) & 1u) ? 0.f : f;
+  return ((fm.both >> (8 * e)) & 1u) ? val : keep;
+}
+__device__ __forceinline__ double2 gc_sel2(unsigned fl, int e, double2 v) {
+  return make_double2(((fl >> (8 * e)) & 1u) ? v.x : 0.0, ((fl >> (8 * e + 8)) & 1u) ? v.y : 0.0);
+}
+
+constexpr int GC_TY = 8;
+struct GcSmem {
+  double p[2][GC_TY + 2][128];      // rows j0-1 .. j0+GC_TY
+  unsigned m[2][GC_TY + 2][32];     // labels, one quad per word
+};
+
+__global__ void __launch_bounds__(32 * GC_TY, 3)
+k_grad_check4(Geo g, const uint8_t* __restrict__ media, const uint8_t* __restrict__ codes,
+              const double* __restrict__ p, const float* __restrict__ u,
+              const float* __restrict__ v, const float* __restrict__ w, float* __restrict__ u2,
+              float* __restrict__ v2, float* __restrict__ w2, double kappa, Scal* __restrict__ sc,
+              double* __restrict__ partials, int zchunk) {
+  __shared__ GcSmem sm;
+  __shared__ double red[32];
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 128 + 4 * lane, j = blockIdx.y * GC_TY + ty;
+  const int kb = blockIdx.z * zchunk, ke = min(kb + zchunk, g.nz);
+  const bool act = i < g.nx && j < g.ny;
+  const bool has_xl = act && i > 0, has_xr = act && i + 4 < g.nx;
+  const bool row_lo = (ty == 0), row_hi = (ty == GC_TY - 1);
+  const bool lo_in = i < g.nx && j >= 1 && j - 1 < g.ny;        // row j-1 is a row of the box
+  const bool hi_in = i < g.nx && j + 1 < g.ny;
+  const unsigned ABS4 = 0xffffffffu;                            // four ABSENT labels
+  const double2 Z2 = make_double2(0.0, 0.0);
+  const float4 Z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long idx = ((long long)kb * g.ny + j) * g.nx + i;
+  float mx = 0.f;
+  unsigned bad = 0;
+
+  // The shared tile of plane k+1 is written during iteration k (own row: this iteration's +z
+  // loads; halo rows: loaded by the CTA's edge rows one plane ahead), so the barrier at the top
+  // of an iteration never waits for a load issued in that iteration, and nothing but the new w
+  // of plane k-1 is carried in registers.  Pressures enter the tile as 0 on non-Fluid cells.
+  const bool edge = row_lo || row_hi;                 // GC_TY > 1: never both
+  const bool edge_in = row_lo ? lo_in : hi_in;
+  const long long eoff = row_lo ? -(long long)g.nx : (long long)g.nx;
+  const int erow = row_lo ? 0 : GC_TY + 1;
+  float wprev[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    unsigned m_c = ABS4;
+    double2 pc0 = Z2, pc1 = Z2;
+    if (act) {
+      m_c = *reinterpret_cast<const unsigned*>(media + idx);
+      pc0 = *reinterpret_cast<const double2*>(p + idx);
+      pc1 = *reinterpret_cast<const double2*>(p + idx + 2);
+      const unsigned mb = *reinterpret_cast<const unsigned*>(media + idx - g.plane);
+      double2 b0 = *reinterpret_cast<const double2*>(p + idx - g.plane);
+      double2 b1 = *reinterpret_cast<const double2*>(p + idx - g.plane + 2);
+      const float4 wb = *reinterpret_cast<const float4*>(w + idx - g.plane);
+      const unsigned nsb = gc_ns4(mb), flb = mb & nsb, nsc = gc_ns4(m_c), flc = m_c & nsc;
+      b0 = gc_sel2(flb, 0, b0); b1 = gc_sel2(flb, 2, b1);
+      pc0 = gc_sel2(flc, 0, pc0); pc1 = gc_sel2(flc, 2, pc1);
+      const GcFace fz = gc_face4(nsb, flb, nsc, flc);
+      wprev[0] = gc_apply(fz, 0, b0.x, pc0.x, wb.x, kappa);
+      wprev[1] = gc_apply(fz, 1, b0.y, pc0.y, wb.y, kappa);
+      wprev[2] = gc_apply(fz, 2, b1.x, pc1.x, wb.z, kappa);
+      wprev[3] = gc_apply(fz, 3, b1.y, pc1.y, wb.w, kappa);
+    }
+    sm.m[0][ty + 1][lane] = m_c;
+    *reinterpret_cast<double2*>(&sm.p[0][ty + 1][4 * lane]) = pc0;
+    *reinterpret_cast<double2*>(&sm.p[0][ty + 1][4 * lane + 2]) = pc1;
+    if (edge) {
+      unsigned mm = ABS4;
+      double2 a0 = Z2, a1 = Z2;
+      if (edge_in) {
+        mm = *reinterpret_cast<const unsigned*>(media + idx + eoff);
+        a0 = *reinterpret_cast<const double2*>(p + idx + eoff);
+        a1 = *reinterpret_cast<const double2*>(p + idx + eoff + 2);
+        const unsigned f = mm & gc_ns4(mm);
+        a0 = gc_sel2(f, 0, a0); a1 = gc_sel2(f, 2, a1);
+      }
+      sm.m[0][erow][lane] = mm;
+      *reinterpret_cast<double2*>(&sm.p[0][erow][4 * lane]) = a0;
+      *reinterpret_cast<double2*>(&sm.p[0][erow][4 * lane + 2]) = a1;
+    }
+  }
+
+  for (int k = kb; k < ke; ++k, idx += g.plane) {
+    const int b = (k - kb) & 1;
+    // ---- this plane's loads (none is needed before the barrier) -----------------------------------
+    unsigned c4 = 0, m_n = ABS4, mxl = ABSENT, mxr = ABSENT, hm = ABS4;
+    float4 u4 = Z4, v4 = Z4, w4 = Z4, vq = Z4;
+    double2 pn0 = Z2, pn1 = Z2, h0 = Z2, h1 = Z2;
+    double pxl = 0.0, pxr = 0.0;
+    float uxl = 0.f;
+    if (act) {
+      c4 = *reinterpret_cast<const unsigned*>(codes + idx);
+      u4 = *reinterpret_cast<const float4*>(u + idx);
+      v4 = *reinterpret_cast<const float4*>(v + idx);
+      w4 = *reinterpret_cast<const float4*>(w + idx);
+      m_n = *reinterpret_cast<const unsigned*>(media + idx + g.plane);
+      pn0 = *reinterpret_cast<const double2*>(p + idx + g.plane);
+      pn1 = *reinterpret_cast<const double2*>(p + idx + g.plane + 2);
+      if (j > 0) vq = *reinterpret_cast<const float4*>(v + idx - g.nx);   // old v of row j-1
+      if (lane == 0 && has_xl) { mxl = media[idx - 1]; pxl = p[idx - 1]; uxl = u[idx - 1]; }
+      if (lane == 31 && has_xr) { mxr = media[idx + 4]; pxr = p[idx + 4]; }
+    }
+    if (edge && edge_in) {                            // halo row of plane k+1
+      hm = *reinterpret_cast<const unsigned*>(media + idx + g.plane + eoff);
+      h0 = *reinterpret_cast<const double2*>(p + idx + g.plane + eoff);
+      h1 = *reinterpret_cast<const double2*>(p + idx + g.plane + eoff + 2);
+    }
+    __syncthreads();
+    // ---- label masks of the quad and of its +x, +y, +z, -y neighbours -----------------------------
+    const unsigned m_c = sm.m[b][ty + 1][lane];
+    if (lane < 31) {
+      mxr = sm.m[b][ty + 1][lane + 1] & 0xffu;
+      pxr = sm.p[b][ty + 1][4 * lane + 4];
+    } else {
+      pxr = (mxr == (unsigned)FLUID) ? pxr : 0.0;
+    }
+    const unsigned ns0 = gc_ns4(m_c), fl0 = m_c & ns0;
+    const unsigned m_x = (m_c >> 8) | (mxr << 24);            // labels of cells 1 .. 4
+    const unsigned nsx = gc_ns4(m_x), flx = m_x & nsx;
+    const unsigned nsz = gc_ns4(m_n), flz = m_n & nsz;
+    const GcFace fx = gc_face4(ns0, fl0, nsx, flx), fzf = gc_face4(ns0, fl0, nsz, flz);
+    pn0 = gc_sel2(flz, 0, pn0); pn1 = gc_sel2(flz, 2, pn1);
+    double px[5];
+    {
+      const double2 a0 = *reinterpret_cast<const double2*>(&sm.p[b][ty + 1][4 * lane]);
+      const double2 a1 = *reinterpret_cast<const double2*>(&sm.p[b][ty + 1][4 * lane + 2]);
+      px[0] = a0.x; px[1] = a0.y; px[2] = a1.x; px[3] = a1.y; px[4] = pxr;
+    }
+    float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    float ww[4] = {w4.x, w4.y, w4.z, w4.w}, vm[4];
+    const unsigned cc[4] = {c4 & 0xffu, (c4 >> 8) & 0xffu, (c4 >> 16) & 0xffu, c4 >> 24};
+    {
+      const double pz[4] = {pn0.x, pn0.y, pn1.x, pn1.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uu[e] = gc_apply(fx, e, px[e], px[e + 1], uu[e], kappa);
+        ww[e] = gc_apply(fzf, e, px[e], pz[e], ww[e], kappa);
+      }
+    }
+    {
+      const unsigned my4 = sm.m[b][ty + 2][lane];
+      const unsigned nsy = gc_ns4(my4), fly = my4 & nsy;
+      const GcFace fy = gc_face4(ns0, fl0, nsy, fly);
+      const double2 y0 = *reinterpret_cast<const double2*>(&sm.p[b][ty + 2][4 * lane]);
+      const double2 y1 = *reinterpret_cast<const double2*>(&sm.p[b][ty + 2][4 * lane + 2]);
+      const double py[4] = {y0.x, y0.y, y1.x, y1.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) vv[e] = gc_apply(fy, e, px[e], py[e], vv[e], kappa);
+    }
+    {   // incoming y face: the new v of row j-1 (quad_div reads it only under B_YM)
+      const unsigned mq4 = sm.m[b][ty][lane];
+      const unsigned nsq = gc_ns4(mq4), flq = mq4 & nsq;
+      const GcFace fq = gc_face4(nsq, flq, ns0, fl0);
+      const double2 q0 = *reinterpret_cast<const double2*>(&sm.p[b][ty][4 * lane]);
+      const double2 q1 = *reinterpret_cast<const double2*>(&sm.p[b][ty][4 * lane + 2]);
+      const double pq[4] = {q0.x, q0.y, q1.x, q1.y};
+      const float vqa[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) vm[e] = gc_apply(fq, e, pq[e], px[e], vqa[e], kappa);
+    }
+    // incoming x face of cell 0: the new u of the cell on the left
+    float ul = __shfl_up_sync(0xffffffffu, uu[3], 1);
+    if (lane == 0)
+      ul = has_xl ? grad_face((uint8_t)mxl, (uint8_t)(m_c & 0xffu), pxl, px[0], uxl, kappa) : 0.f;
+    if (act) {
+      *reinterpret_cast<float4*>(u2 + idx) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+      *reinterpret_cast<float4*>(v2 + idx) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      *reinterpret_cast<float4*>(w2 + idx) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+      // ---- validators (k_check4) on the new faces ---------------------------------------------
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        bad += !isfinite(uu[e]) + !isfinite(vv[e]) + !isfinite(ww[e]);
+      if (c4 & 0x40404040u) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (cc[e] & B_FLUID) {
+            bad += !isfinite(px[e]);
+            const float d = fabsf(quad_div(cc[e], uu[e], e ? uu[e - 1] : ul, vv[e], vm[e], ww[e],
+                                           wprev[e]));
+            if (d == d) mx = fmaxf(mx, d);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wprev[e] = ww[e];
+    // the next plane's own row (read after the next barrier; buffer b ^ 1 was last read before
+    // this iteration's barrier)
+    sm.m[b ^ 1][ty + 1][lane] = m_n;
+    *reinterpret_cast<double2*>(&sm.p[b ^ 1][ty + 1][4 * lane]) = pn0;
+    *reinterpret_cast<double2*>(&sm.p[b ^ 1][ty + 1][4 * lane + 2]) = pn1;
+    if (edge) {
+      const unsigned f = hm & gc_ns4(hm);
+      sm.m[b ^ 1][erow][lane] = hm;
+      *reinterpret_cast<double2*>(&sm.p[b ^ 1][erow][4 * lane]) = gc_sel2(f, 0, h0);
+      *reinterpret_cast<double2*>(&sm.p[b ^ 1][erow][4 * lane + 2]) = gc_sel2(f, 2, h1);
+    }
+  }
+  const double bm = block_max((double)mx, red);
+  const double bb = block_sum((double)bad, red);
+  const unsigned nb = num_blocks();
+  if (lane == 0 && ty == 0) {
+    partials[linear_block()] = bm;
+    if (bb > 0.0) atomicAdd(&sc->nonfinite, (unsigned long long)bb);
+  }
+  if (last_block(&sc->ticketC, nb)) {
+    const unsigned tid = lane + 32 * ty;
+    double t = 0.0;
+    for (unsigned q = tid; q < nb; q += 32 * GC_TY) t = fmax(t, __ldcg(partials + q));
+    t = block_max(t, red);
+    if (tid == 0) sc->gD[sc->rank] = t;
+  }
+}
+
 // ---- true residual (iterative refinement of the fp32 solve) -----------------------------
 // r = b - A x with x the fp64 pressure accumulator and the stencil evaluated in fp64:
 // the recursive residual of PCG drifts from the true one by ~eps32 |A| |x| (the search

@@ -767,32 +767,76 @@ def test_phase_a_variants_are_bit_identical(shape, monkeypatch):
         assert np.abs(got[n] - res[0][1][n]).max() <= 1e-5 * vscale(res[0][1][n]), n
 
 
-@pytest.mark.parametrize("shape", [(64, 24, 12), (8, 5, 3), (132, 9, 1)])
+@pytest.mark.parametrize("shape", [(64, 24, 12), (8, 5, 3), (132, 9, 1), (260, 37, 21),
+                                   (128, 8, 40), (8, 2, 2)])
 def test_quad_kernels_equal_the_one_cell_kernels_bit_for_bit(shape, monkeypatch):
-    """k_div_rhs4 / k_grad_sub4 / k_check4 (fp32, nx % 4 = 0) against the generic kernels
-    on random labels (every branch of the label logic), and against the oracle."""
+    """k_div_rhs4 / k_grad_sub4 / k_check4 and the one-pass k_grad_check4 (fp32, nx % 4 = 0)
+    against the generic kernels on random labels (every branch of the label logic; several
+    x tiles, ragged y tiles, several z chunks), and against the oracle."""
     nx, ny, nz = shape
     sc = scenes.random_box(nx, ny, nz, seed=9, dtype=np.float32, p_solid=0.2, p_air=0.3,
                            absent_border=True)
     lab, U, V, W = fields(sc, np.float32)
     res = {}
-    for quad in ("0", "1"):
-        monkeypatch.setenv("SPL_NO_QUAD", "0" if quad == "1" else "1")
+    for mode, env in (("0", {"SPL_NO_QUAD": "1"}), ("1", {"SPL_NO_QUAD": "0", "SPL_NO_GC_FUSE": "1"}),
+                      ("f", {"SPL_NO_QUAD": "0", "SPL_NO_GC_FUSE": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         with solver_for(sc, dtype=np.float32, tol=1e-6, max_iters=400) as s:
             s.upload(lab, U, V, W)
             div = s.download(div=True)["div"]
             s.set_fixed_iters(25)
             info = s.project(sc["dt"])
-            res[quad] = (div, s.download(), info)
+            res[mode] = (div, s.download(), info)
     d0, g0, i0 = res["0"]
     d1, g1, i1 = res["1"]
-    assert np.array_equal(d0, d1)
-    for n in "UVWP":
-        assert np.array_equal(g0[n], g1[n]), n
-    assert i0["max_abs_div"] == i1["max_abs_div"] and i0["nonfinite"] == i1["nonfinite"]
+    for mode in ("1", "f"):
+        dm, gm, im = res[mode]
+        assert np.array_equal(d0, dm), mode
+        for n in "UVWP":
+            assert np.array_equal(g0[n], gm[n]), (mode, n)
+        assert i0["max_abs_div"] == im["max_abs_div"] and i0["nonfinite"] == im["nonfinite"], mode
+    assert res["f"][2]["kernel_launches"] == i1["kernel_launches"] - 1   # one pass instead of two
     want = dr.divergence(lab, U.astype(np.float64), V.astype(np.float64), W.astype(np.float64))
     fl = lab == dr.FLUID                                 # div is reported on Fluid cells
     assert np.abs(d1 - want)[fl].max() <= 1e-6 * vscale(U, V, W) and np.all(d1[~fl] == 0)
+
+
+@pytest.mark.parametrize("shape", [(64, 48, 24), (8, 5, 3), (132, 9, 2), (36, 20, 12)])
+def test_rbic0_quad_sweeps_equal_the_one_cell_sweeps(shape, monkeypatch):
+    """k_rb_black4 / k_rb_red4 (fp32, nx % 4 = 0) against k_rb_sweep on random labels: z = M^-1 r
+    is bit for bit the same, so after K fixed iterations the two solves differ only through the
+    summation order of r.z (<= 1e-5 relative on p, u, v, w); and the quad path converges in the
+    oracle's iteration count (fp64 numpy apply_rbic0) to the direct solve."""
+    nx, ny, nz = shape
+    sc = scenes.random_box(nx, ny, nz, seed=21, dtype=np.float32, p_solid=0.15, p_air=0.3)
+    lab = open_pockets(sc["labels"])
+    _, U, V, W = fields(sc, np.float32)
+    res = {}
+    for quad in ("0", "1"):
+        monkeypatch.setenv("SPL_NO_QUAD", "0" if quad == "1" else "1")
+        with solver_for(sc, dtype=np.float32, tol=1e-6, max_iters=2000, precond="rbic0") as s:
+            s.upload(lab, U, V, W)
+            s.set_fixed_iters(6)
+            info = s.project(sc["dt"])
+            res[quad] = (s.download(), info)
+    (g0, i0), (g1, i1) = res["0"], res["1"]
+    assert i0["iters"] == i1["iters"] == 6
+    assert abs(i0["r_inf"] - i1["r_inf"]) <= 1e-4 * i0["b_inf"]
+    for n in "UVWP":
+        assert np.abs(g0[n] - g1[n]).max() <= 1e-5 * vscale(g0[n]), n
+    monkeypatch.setenv("SPL_NO_QUAD", "0")
+    f64 = [a.astype(np.float64) for a in (U, V, W)]
+    with solver_for(sc, dtype=np.float32, tol=1e-6, max_iters=2000, precond="rbic0") as s:
+        s.upload(lab, U, V, W)
+        info = s.project(sc["dt"])
+        got = s.download()
+    b = dr.rhs(lab, *f64, sc["dt"], sc["h"], sc["rho"])
+    _, oinfo = dr.pcg(lab, b, dr.PC_RBIC0, tol=1e-6)
+    assert info["converged"] == 1 and abs(info["iters"] - oinfo["iters"]) <= 3, (info, oinfo)
+    U2, V2, W2, P, _ = dr.project(lab, *f64, sc["dt"], sc["h"], sc["rho"], direct=True)
+    for n, r in (("U", U2), ("V", V2), ("W", W2)):
+        assert np.abs(got[n] - r).max() <= 5e-4 * vscale(U2, V2, W2), n
 
 
 # --------------------------------------------------------------------------
