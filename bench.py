@@ -45,6 +45,7 @@ BYTES_ADVECT = 25      # u,v,w 12 + label 1 -> u',v',w' 12                 (SURV
 BYTES_RHS = 17         # u,v,w 12 + code 1 -> b 4
 BYTES_GRAD = 33        # p 8 (fp64) + label 1 + u,v,w 12 -> u,v,w 12
 BYTES_CHECK = 21       # u,v,w 12 + p 8 + code 1
+BYTES_GRADCHECK = 34   # one pass (k_grad_check4): label 1 + code 1 + p 8 + u,v,w 12 -> u,v,w 12
 
 
 def parse_args():
@@ -92,6 +93,26 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gpu_numa_cpus(gpu_index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader",
+                              "-i", str(gpu_index)], capture_output=True, text=True,
+                             timeout=20).stdout.strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                       # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return (node, cpus & os.sched_getaffinity(0)) if cpus & os.sched_getaffinity(0) else None
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -354,13 +375,28 @@ def run_cuda(args):
                       z0=rank * nz, nccl_id=D.nccl_id())
 
     s = make(args.precond)
-    # pinned host buffers (the e2e leg copies from / to these every step)
+    # pinned host buffers (the e2e leg copies from / to these every step), allocated and first
+    # touched on the GPU's own NUMA node: with one rank per GPU the copies of the 8 ranks then
+    # do not all cross the socket interconnect
+    numa = gpu_numa_cpus(local)
+    old_aff = os.sched_getaffinity(0)
+    if numa:
+        try:
+            os.sched_setaffinity(0, numa[1])
+        except Exception:
+            numa = None
     hin = {k: PinnedArray(shape, np.float32) for k in "UVW"}
     hlab = PinnedArray(shape, np.uint8)
     hout = {k: PinnedArray(shape, np.float32) for k in "UVWP"}
+    hout2 = {k: PinnedArray(shape, np.float32) for k in "UVWP"}    # second box in flight
     for k in "UVW":
         hin[k].array[...] = sc[k]
     hlab.array[...] = sc["labels"]
+    for hb in (hout, hout2):
+        for k in "UVWP":
+            hb[k].array[...] = 0
+    if numa:
+        os.sched_setaffinity(0, old_aff)
     del sc
     ptr = lambda a: C.c_void_p(a.array.ctypes.data)
 
@@ -389,9 +425,49 @@ def run_cuda(args):
         s.step(dt)
         s.download_ptrs(ptr(hout["U"]), ptr(hout["V"]), ptr(hout["W"]), ptr(hout["P"]))
     D.barrier()
-    e2e_s = D.max(time.perf_counter() - t0) / args.steps
-    e2e_value = cells / e2e_s
+    e2e_one_s = D.max(time.perf_counter() - t0) / args.steps
     checksum = float(hout["P"].array[nz // 2, ny // 2, ::64].astype(np.float64).sum())
+    # The same K steps with TWO boxes in flight per GPU (a second context; every step still
+    # uploads its inputs from and downloads its result to pinned host memory): the copies of one
+    # box ride on its copy streams while the other box's step runs.  One host thread, so the
+    # collectives of the slab contexts are issued in the same order on every rank.
+    e2e_mode = "two boxes in flight per GPU (spl_upload_async / spl_step / spl_download_async)"
+    e2e_s = e2e_one_s
+    e2e_match = True
+    e2e_step_dev_ms = None
+    if os.environ.get("SPL_BENCH_E2E", "pipelined") != "pipelined":
+        e2e_mode = "one box: upload, step, download in sequence"
+    else:
+        s2 = make(args.precond)
+        s2.set_fixed_iters(args.pcg_iters)
+        boxes = [(s, hout), (s2, hout2)]
+        up = lambda b: b.upload_async_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
+
+        def run(n):
+            dev = 0.0
+            up(boxes[0][0])
+            for i in range(n):
+                b, out = boxes[i % 2]
+                if i + 1 < n:
+                    up(boxes[(i + 1) % 2][0])
+                dev += b.step(dt)["ms_total"]
+                b.download_async_ptrs(ptr(out["U"]), ptr(out["V"]), ptr(out["W"]), ptr(out["P"]))
+            for b, _ in boxes:
+                b.sync()
+            return dev / n
+
+        run(2)
+        D.barrier()
+        t0 = time.perf_counter()
+        e2e_step_dev_ms = run(args.steps)
+        D.barrier()
+        e2e_s = D.max(time.perf_counter() - t0) / args.steps
+        last = boxes[(args.steps - 1) % 2][1]
+        checksum2 = float(last["P"].array[nz // 2, ny // 2, ::64].astype(np.float64).sum())
+        e2e_match = checksum2 == checksum      # the same box through either path
+        s2.close()
+        s2 = None
+    e2e_value = cells / e2e_s
 
     # ---- per-kernel roofline: CUDA events around every PCG launch -------------------------
     s.restore()
@@ -402,9 +478,15 @@ def run_cuda(args):
     gbs_a, gbs_b, gbs_x = gbs(BYTES_PHASE_A, ms_a), gbs(BYTES_PHASE_B, ms_b), gbs(BYTES_XFLUSH, ms_x)
     dom = "k_phaseB" if ms_b >= ms_a else "k_phaseA_tma"
     dom_gbs = gbs_b if dom == "k_phaseB" else gbs_a
-    step_bpc = BYTES_ADVECT + BYTES_RHS + BYTES_GRAD + BYTES_CHECK + args.pcg_iters * BYTES_ITER
+    # gradient + validators: one marching pass unless SPL_NO_GC_FUSE / SPL_NO_QUAD ask for two
+    gc_fused = (args.n % 4 == 0 and os.environ.get("SPL_NO_GC_FUSE", "0") in ("", "0")
+                and os.environ.get("SPL_NO_QUAD", "0") in ("", "0"))
+    bytes_gc = BYTES_GRADCHECK if gc_fused else BYTES_GRAD + BYTES_CHECK
+    step_bpc = BYTES_ADVECT + BYTES_RHS + bytes_gc + args.pcg_iters * BYTES_ITER
     step_gbs = gbs(step_bpc, ms_per_step)
-    nonpcg_ms = stage["ms_advect"] + stage["ms_rhs"] + stage["ms_grad"]
+    ms_gc = stage["ms_grad"] + stage["ms_check"]
+    nonpcg_ms = stage["ms_advect"] + stage["ms_rhs"] + ms_gc
+    nonpcg_bpc = BYTES_ADVECT + BYTES_RHS + bytes_gc
     kernels = {
         "k_phaseA_tma": {"ms": ms_a, "bytes_per_cell": BYTES_PHASE_A, "GBps": gbs_a, "frac": gbs_a / peak},
         "k_phaseB": {"ms": ms_b, "bytes_per_cell": BYTES_PHASE_B, "GBps": gbs_b, "frac": gbs_b / peak},
@@ -420,16 +502,18 @@ def run_cuda(args):
         "rhs (k_div_rhs4)": {"ms": stage["ms_rhs"], "bytes_per_cell": BYTES_RHS,
                              "GBps": gbs(BYTES_RHS, stage["ms_rhs"]),
                              "frac": gbs(BYTES_RHS, stage["ms_rhs"]) / peak},
-        "grad (k_grad_sub4)": {"ms": stage["ms_grad"], "bytes_per_cell": BYTES_GRAD,
-                               "GBps": gbs(BYTES_GRAD, stage["ms_grad"]),
-                               "frac": gbs(BYTES_GRAD, stage["ms_grad"]) / peak},
-        "check (k_check4)": {"ms": stage["ms_check"], "bytes_per_cell": BYTES_CHECK,
-                             "GBps": gbs(BYTES_CHECK, stage["ms_check"]),
-                             "frac": gbs(BYTES_CHECK, stage["ms_check"]) / peak},
-        "non_pcg (advect + rhs + grad)": {
-            "ms": nonpcg_ms, "bytes_per_cell": BYTES_ADVECT + BYTES_RHS + BYTES_GRAD,
-            "GBps": gbs(BYTES_ADVECT + BYTES_RHS + BYTES_GRAD, nonpcg_ms),
-            "frac": gbs(BYTES_ADVECT + BYTES_RHS + BYTES_GRAD, nonpcg_ms) / peak},
+        **({"grad + check (k_grad_check4)": {
+                "ms": ms_gc, "bytes_per_cell": BYTES_GRADCHECK, "GBps": gbs(BYTES_GRADCHECK, ms_gc),
+                "frac": gbs(BYTES_GRADCHECK, ms_gc) / peak}} if gc_fused else {
+            "grad (k_grad_sub4)": {"ms": stage["ms_grad"], "bytes_per_cell": BYTES_GRAD,
+                                   "GBps": gbs(BYTES_GRAD, stage["ms_grad"]),
+                                   "frac": gbs(BYTES_GRAD, stage["ms_grad"]) / peak},
+            "check (k_check4)": {"ms": stage["ms_check"], "bytes_per_cell": BYTES_CHECK,
+                                 "GBps": gbs(BYTES_CHECK, stage["ms_check"]),
+                                 "frac": gbs(BYTES_CHECK, stage["ms_check"]) / peak}}),
+        "non_pcg (advect + rhs + grad + check)": {
+            "ms": nonpcg_ms, "bytes_per_cell": nonpcg_bpc,
+            "GBps": gbs(nonpcg_bpc, nonpcg_ms), "frac": gbs(nonpcg_bpc, nonpcg_ms) / peak},
     }
 
     # ---- one run-to-tolerance step (iteration count) ------------------------
@@ -537,7 +621,12 @@ def run_cuda(args):
             "wall_ms_per_step": main["wall_ms_per_step"],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_s * 1e3,
-                    "result_checksum": checksum},
+                    "result_checksum": checksum, "mode": e2e_mode,
+                    "same_result_as_one_box": e2e_match,
+                    "step_device_ms": e2e_step_dev_ms,
+                    "one_box": {"value": cells / e2e_one_s, "ms_per_step": e2e_one_s * 1e3,
+                                "mode": "upload, step, download of ONE box in sequence"},
+                    "pinned_numa_node": numa[0] if numa else None},
             "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak,
                          "unit": "GB/s", "frac": dom_gbs / peak,

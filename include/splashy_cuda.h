@@ -132,6 +132,20 @@ int  spl_upload(spl_ctx* ctx, const uint8_t* media, const void* u,
 /* device -> host; every pointer may be NULL.  div = (incoming - outgoing) of
  * Pressure.fs:16-32 for the current velocities (0 on non-Fluid cells).      */
 int  spl_download(spl_ctx* ctx, void* u, void* v, void* w, void* p, void* div);
+/* The same two transfers without waiting for them (PINNED host buffers): the copies are
+ * queued on per-context copy streams, one per direction, and the call returns.
+ * spl_upload_async: the next entry point that needs the state (spl_step, ...) waits for
+ * the copies on the device and then builds the label-derived data; the host buffers must
+ * stay untouched until then.  spl_download_async: spl_sync waits for it.  The copies of
+ * one context overlap the kernels of another: with two boxes in flight per GPU
+ *     upload_async(B); step(A); download_async(A); upload_async(A'); step(B); ...
+ * the PCIe time of Grid <-> device (Grid.fs:38,49-59 in, update_velocities /
+ * update_pressures out) hides behind the other box's step.  Every collective of a slab
+ * context stays on its compute stream, in program order.                              */
+int  spl_upload_async(spl_ctx* ctx, const uint8_t* media, const void* u,
+                      const void* v, const void* w, const void* p);
+int  spl_download_async(spl_ctx* ctx, void* u, void* v, void* w, void* p);
+int  spl_sync(spl_ctx* ctx);
 
 /* Cell-centred scalar fields carried by the flow (north_star: "semi-Lagrangian advection of
  * the staggered MAC velocity and scalar fields"; SURVEY 8d cfg2 "one scalar phi", +8 B/cell).

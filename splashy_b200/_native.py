@@ -79,6 +79,9 @@ SYMBOLS = {
     "spl_nccl_unique_id": (C.c_int, [_VP]),
     "spl_upload": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "spl_download": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "spl_upload_async": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "spl_download_async": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "spl_sync": (C.c_int, [_VP]),
     "spl_set_scalars": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
     "spl_get_scalars": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
     "spl_advect": (C.c_int, [_VP, C.c_double, C.POINTER(SplInfo)]),

@@ -193,6 +193,11 @@ struct spl_ctx {
   // chunks of phase A run (SPL_OVERLAP=0: everything on one stream); the per-rank CG scalars
   // are exchanged by peer-to-peer stores into IPC-mapped boxes (SPL_P2P=0: ncclAllGather)
   cudaStream_t cstream = nullptr;
+  // spl_upload_async / spl_download_async: one copy stream per direction (PCIe is full duplex)
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_down = nullptr, ev_done = nullptr;
+  bool upload_pending = false;   // copies are queued on h2d; the label-derived data is not built yet
+  bool download_queued = false;  // ev_down marks the end of the last queued download
   cudaEvent_t ev_beta = nullptr, ev_halo = nullptr;
   bool overlap = true;
   bool split = false;          // SPL_SPLIT=1: interior / boundary launches of phase A around NCCL send / recv
@@ -269,6 +274,10 @@ struct spl_ctx {
   double rhs_dt = 0.0;
   std::string err;
 };
+
+extern "C" {
+static int finish_upload(spl_ctx* c);   // completes a pending spl_upload_async
+}
 
 namespace {
 
@@ -1316,6 +1325,16 @@ struct Impl {
   }
 };
 
+// entry points that need the uploaded state: completes a pending spl_upload_async first
+#define NEED_UPLOAD(c, who)                                                        \
+  do {                                                                             \
+    if ((c)->upload_pending) {                                                     \
+      const int rc_ = finish_upload(c);                                            \
+      if (rc_) return rc_;                                                         \
+    }                                                                              \
+    if (!(c)->uploaded) return fail(c, SPL_E_STATE, who " before spl_upload");     \
+  } while (0)
+
 #define DISPATCH(c, expr_f32, expr_f64) ((c)->d.dtype == SPL_F64 ? (expr_f64) : (expr_f32))
 
 int do_rhs(spl_ctx* c, double dt) {
@@ -1424,6 +1443,10 @@ void spl_destroy(spl_ctx* c) {
       if (c->nb_maps[side][i]) cudaIpcCloseMemHandle(c->nb_maps[side][i]);
   if (c->pbox) cudaFree(c->pbox);
   if (c->hticket) cudaFree(c->hticket);
+  if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
+  if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
+  for (cudaEvent_t e : {c->ev_up, c->ev_down, c->ev_done})
+    if (e) cudaEventDestroy(e);
   if (c->cstream) cudaStreamDestroy(c->cstream);
   if (c->ev_beta) cudaEventDestroy(c->ev_beta);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
@@ -1830,30 +1853,41 @@ static int rebuild_operators(spl_ctx* c) {
   return SPL_OK;
 }
 
-int spl_upload(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
-               const void* w, const void* p) {
-  if (!c) return SPL_E_BADARG;
-  if (!media) return fail(c, SPL_E_BADARG, "spl_upload: media is required");
-  CU(cudaSetDevice(c->d.device));
+// host -> device copies of one upload on stream `st`
+static int enqueue_upload(spl_ctx* c, cudaStream_t st, const uint8_t* media, const void* u,
+                          const void* v, const void* w, const void* p) {
   const Geo& g = c->g;
   const size_t nb = (size_t)g.ncell * c->esz;
-  CU(cudaMemcpyAsync(c->media, media, (size_t)g.ncell, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->media, media, (size_t)g.ncell, cudaMemcpyHostToDevice, st));
   const void* src[3] = {u, v, w};
   char* dst[3] = {c->u, c->v, c->w};
   for (int i = 0; i < 3; ++i) {
-    if (src[i]) CU(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyHostToDevice, c->stream));
-    else CU(cudaMemsetAsync(dst[i], 0, nb, c->stream));
+    if (src[i]) CU(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(dst[i], 0, nb, st));
   }
   // pressure is kept in fp64 on the device
   if (!p) {
-    CU(cudaMemsetAsync(c->p, 0, (size_t)g.ncell * 8, c->stream));
+    CU(cudaMemsetAsync(c->p, 0, (size_t)g.ncell * 8, st));
   } else if (c->d.dtype == SPL_F64) {
-    CU(cudaMemcpyAsync(c->p, p, (size_t)g.ncell * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->p, p, (size_t)g.ncell * 8, cudaMemcpyHostToDevice, st));
   } else {
-    CU(cudaMemcpyAsync(c->q, p, nb, cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, (k_convert<float, double>), grid_for(c, g.ncell), 256, g.ncell,
-           reinterpret_cast<const float*>(c->q), reinterpret_cast<double*>(c->p));
+    CU(cudaMemcpyAsync(c->q, p, nb, cudaMemcpyHostToDevice, st));
+    k_convert<float, double><<<grid_for(c, g.ncell), 256, 0, st>>>(
+        g.ncell, reinterpret_cast<const float*>(c->q), reinterpret_cast<double*>(c->p));
+    c->launches++;
   }
+  return SPL_OK;
+}
+
+// what follows the copies, on the compute stream: label halos and everything derived from
+// the labels (collectives when world > 1, hence always in program order on c->stream)
+static int finish_upload(spl_ctx* c) {
+  CU(cudaSetDevice(c->d.device));
+  if (c->upload_pending) {
+    CU(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+    c->upload_pending = false;
+  }
+  const Geo& g = c->g;
   int rc = exchange_halo(c, reinterpret_cast<char*>(c->media), 1, ncclUint8, g.hz);
   if (rc) return rc;
   if ((rc = rebuild_operators(c))) return rc;
@@ -1863,26 +1897,82 @@ int spl_upload(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
   return SPL_OK;
 }
 
-int spl_download(spl_ctx* c, void* u, void* v, void* w, void* p, void* div) {
+int spl_upload(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
+               const void* w, const void* p) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_download before spl_upload");
+  if (!media) return fail(c, SPL_E_BADARG, "spl_upload: media is required");
   CU(cudaSetDevice(c->d.device));
+  if (c->h2d) CU(cudaStreamSynchronize(c->h2d));      // an earlier asynchronous upload / download
+  if (c->d2h) CU(cudaStreamSynchronize(c->d2h));
+  c->upload_pending = false;
+  int rc = enqueue_upload(c, c->stream, media, u, v, w, p);
+  if (rc) return rc;
+  return finish_upload(c);
+}
+
+static int async_streams(spl_ctx* c) {
+  if (c->h2d) return SPL_OK;
+  CU(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_down, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+  return SPL_OK;
+}
+
+// spl_upload without waiting: the copies are queued on the context's host-to-device stream
+// and the call returns; the first entry point that needs the state (spl_step, ...) waits for
+// them on the device and builds the label-derived data.  The host buffers (pinned, or the
+// call degenerates to a synchronous copy) must stay untouched until then.  Copies of one
+// context overlap the kernels of ANOTHER context: two boxes in flight per GPU hide the PCIe
+// time of upload -> step -> download behind the step of the other box.
+int spl_upload_async(spl_ctx* c, const uint8_t* media, const void* u, const void* v,
+                     const void* w, const void* p) {
+  if (!c) return SPL_E_BADARG;
+  if (!media) return fail(c, SPL_E_BADARG, "spl_upload_async: media is required");
+  CU(cudaSetDevice(c->d.device));
+  int rc = async_streams(c);
+  if (rc) return rc;
+  // the fields may still be read by kernels of this context or by a queued download
+  CU(cudaEventRecord(c->ev_done, c->stream));
+  CU(cudaStreamWaitEvent(c->h2d, c->ev_done, 0));
+  if (c->download_queued) CU(cudaStreamWaitEvent(c->h2d, c->ev_down, 0));
+  if ((rc = enqueue_upload(c, c->h2d, media, u, v, w, p))) return rc;
+  CU(cudaEventRecord(c->ev_up, c->h2d));
+  c->upload_pending = true;
+  c->uploaded = false;
+  return SPL_OK;
+}
+
+static int enqueue_download(spl_ctx* c, cudaStream_t st, void* u, void* v, void* w, void* p) {
   const size_t nb = (size_t)c->g.ncell * c->esz;
   void* dst[3] = {u, v, w};
   char* src[3] = {c->u, c->v, c->w};
   for (int i = 0; i < 3; ++i)
-    if (dst[i]) CU(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyDeviceToHost, c->stream));
+    if (dst[i]) CU(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyDeviceToHost, st));
   if (p) {
     if (c->d.dtype == SPL_F64) {
-      CU(cudaMemcpyAsync(p, c->p, nb, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpyAsync(p, c->p, nb, cudaMemcpyDeviceToHost, st));
     } else {   // fp64 accumulator -> fp32 at the boundary
-      LAUNCH(c, (k_convert<double, float>), grid_for(c, c->g.ncell), 256, c->g.ncell,
-             reinterpret_cast<const double*>(c->p), reinterpret_cast<float*>(c->q));
-      CU(cudaMemcpyAsync(p, c->q, nb, cudaMemcpyDeviceToHost, c->stream));
+      k_convert<double, float><<<grid_for(c, c->g.ncell), 256, 0, st>>>(
+          c->g.ncell, reinterpret_cast<const double*>(c->p), reinterpret_cast<float*>(c->q));
+      c->launches++;
+      CU(cudaMemcpyAsync(p, c->q, nb, cudaMemcpyDeviceToHost, st));
     }
   }
+  return SPL_OK;
+}
+
+int spl_download(spl_ctx* c, void* u, void* v, void* w, void* p, void* div) {
+  if (!c) return SPL_E_BADARG;
+  NEED_UPLOAD(c, "spl_download");
+  CU(cudaSetDevice(c->d.device));
+  if (c->d2h) CU(cudaStreamSynchronize(c->d2h));      // c->q may hold a queued download's pressure
+  int rc = enqueue_download(c, c->stream, u, v, w, p);
+  if (rc) return rc;
   if (div) {
-    int rc = DISPATCH(c, Impl<float>::rhs(c, 1.0f, c->q), Impl<double>::rhs(c, 1.0, c->q));
+    const size_t nb = (size_t)c->g.ncell * c->esz;
+    rc = DISPATCH(c, Impl<float>::rhs(c, 1.0f, c->q), Impl<double>::rhs(c, 1.0, c->q));
     if (rc) return rc;
     CU(cudaMemcpyAsync(div, c->q, nb, cudaMemcpyDeviceToHost, c->stream));
   }
@@ -1890,9 +1980,35 @@ int spl_download(spl_ctx* c, void* u, void* v, void* w, void* p, void* div) {
   return SPL_OK;
 }
 
+// spl_download (without div) queued on the device-to-host stream; spl_sync waits for it.
+int spl_download_async(spl_ctx* c, void* u, void* v, void* w, void* p) {
+  if (!c) return SPL_E_BADARG;
+  NEED_UPLOAD(c, "spl_download_async");
+  CU(cudaSetDevice(c->d.device));
+  int rc = async_streams(c);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev_done, c->stream));
+  CU(cudaStreamWaitEvent(c->d2h, c->ev_done, 0));
+  if ((rc = enqueue_download(c, c->d2h, u, v, w, p))) return rc;
+  CU(cudaEventRecord(c->ev_down, c->d2h));
+  c->download_queued = true;
+  return SPL_OK;
+}
+
+// waits for every queued copy of this context (not for a pending upload's derived data:
+// that is built by the next entry point that needs it)
+int spl_sync(spl_ctx* c) {
+  if (!c) return SPL_E_BADARG;
+  CU(cudaSetDevice(c->d.device));
+  if (c->h2d) CU(cudaStreamSynchronize(c->h2d));
+  if (c->d2h) CU(cudaStreamSynchronize(c->d2h));
+  c->download_queued = false;
+  return SPL_OK;
+}
+
 int spl_advect(spl_ctx* c, double dt, spl_info* info) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_advect before spl_upload");
+  NEED_UPLOAD(c, "spl_advect");
   CU(cudaSetDevice(c->d.device));
   c->launches = 0;
   CU(cudaMemsetAsync(&c->sc->escapes, 0, sizeof(unsigned long long), c->stream));
@@ -1920,7 +2036,7 @@ int spl_advect(spl_ctx* c, double dt, spl_info* info) {
 
 int spl_set_scalars(spl_ctx* c, int n, const void* const* fields) {
   if (!c || n < 0 || n > SPL_MAX_SCALARS || (n > 0 && !fields)) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_set_scalars before spl_upload");
+  NEED_UPLOAD(c, "spl_set_scalars");
   CU(cudaSetDevice(c->d.device));
   int rc;
   while ((int)c->scal.size() < n) {
@@ -1954,7 +2070,7 @@ int spl_get_scalars(spl_ctx* c, int n, void* const* fields) {
 
 int spl_add_forces(spl_ctx* c, double dt) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_add_forces before spl_upload");
+  NEED_UPLOAD(c, "spl_add_forces");
   CU(cudaSetDevice(c->d.device));
   int rc = DISPATCH(c, Impl<float>::forces(c, dt), Impl<double>::forces(c, dt));
   if (rc) return rc;
@@ -1965,7 +2081,7 @@ int spl_add_forces(spl_ctx* c, double dt) {
 
 int spl_add_viscosity(spl_ctx* c, double dt) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_add_viscosity before spl_upload");
+  NEED_UPLOAD(c, "spl_add_viscosity");
   CU(cudaSetDevice(c->d.device));
   int rc = DISPATCH(c, Impl<float>::viscosity(c, dt), Impl<double>::viscosity(c, dt));
   if (rc) return rc;
@@ -1976,7 +2092,7 @@ int spl_add_viscosity(spl_ctx* c, double dt) {
 
 int spl_cleanup(spl_ctx* c) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_cleanup before spl_upload");
+  NEED_UPLOAD(c, "spl_cleanup");
   CU(cudaSetDevice(c->d.device));
   int rc = DISPATCH(c, Impl<float>::cleanup(c), Impl<double>::cleanup(c));
   if (rc) return rc;
@@ -1987,7 +2103,7 @@ int spl_cleanup(spl_ctx* c) {
 
 int spl_divergence(spl_ctx* c, double dt, spl_info* info) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_divergence before spl_upload");
+  NEED_UPLOAD(c, "spl_divergence");
   if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
   CU(cudaSetDevice(c->d.device));
   c->launches = 0;
@@ -2096,13 +2212,13 @@ static int project_impl(spl_ctx* c, double dt, spl_info* info, bool with_advect)
 
 int spl_project(spl_ctx* c, double dt, spl_info* info) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_project before spl_upload");
+  NEED_UPLOAD(c, "spl_project");
   return project_impl(c, dt, info, false);
 }
 
 int spl_step(spl_ctx* c, double dt, spl_info* info) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_step before spl_upload");
+  NEED_UPLOAD(c, "spl_step");
   return project_impl(c, dt, info, true);
 }
 
@@ -2112,6 +2228,7 @@ static bool integral_h(const spl_ctx* c) {
 }
 
 static int markers_need(spl_ctx* c, const char* who) {
+  if (c->upload_pending) { const int rc_ = finish_upload(c); if (rc_) return rc_; }
   if (!c->uploaded) return fail(c, SPL_E_STATE, "%s before spl_upload", who);
   if (!integral_h(c))   // Coord.nearest works on int<m> (Coord.fs:49-57, Constants.fs:11 h = 10)
     return fail(c, SPL_E_BADARG, "%s: the marker stage needs an integral cell size h >= 1", who);
@@ -2257,7 +2374,7 @@ int spl_relabel(spl_ctx* c, int sanity) {
 
 int spl_download_media(spl_ctx* c, uint8_t* media) {
   if (!c || !media) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_download_media before spl_upload");
+  NEED_UPLOAD(c, "spl_download_media");
   CU(cudaSetDevice(c->d.device));
   CU(cudaMemcpyAsync(media, c->media, (size_t)c->g.ncell, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -2266,7 +2383,7 @@ int spl_download_media(spl_ctx* c, uint8_t* media) {
 
 int spl_advance(spl_ctx* c, double dt, int sanity, spl_info* info) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_advance before spl_upload");
+  NEED_UPLOAD(c, "spl_advance");
   if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
   CU(cudaSetDevice(c->d.device));
   int rc = SPL_OK;
@@ -2307,7 +2424,7 @@ int spl_advance(spl_ctx* c, double dt, int sanity, spl_info* info) {
 
 int spl_check(spl_ctx* c, double div_tol, spl_info* info) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_check before spl_upload");
+  NEED_UPLOAD(c, "spl_check");
   CU(cudaSetDevice(c->d.device));
   c->launches = 0;
   CU(cudaMemsetAsync(&c->sc->nonfinite, 0, sizeof(unsigned long long), c->stream));
@@ -2339,7 +2456,7 @@ void spl_host_free(void* p) {
 
 int spl_snapshot(spl_ctx* c) {
   if (!c) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_snapshot before spl_upload");
+  NEED_UPLOAD(c, "spl_snapshot");
   CU(cudaSetDevice(c->d.device));
   if (!c->have_snapshot) {
     int rc;
@@ -2389,7 +2506,7 @@ int spl_timer_stop(spl_ctx* c, float* ms) {
 
 int spl_apply_preconditioner(spl_ctx* c, const void* r, void* z, float* ms) {
   if (!c || !r || !z) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_apply_preconditioner before spl_upload");
+  NEED_UPLOAD(c, "spl_apply_preconditioner");
   if (c->d.precond != SPL_PC_RBIC0 && c->d.precond != SPL_PC_MG)
     return fail(c, SPL_E_BADARG, "preconditioner %d has no stored z", c->d.precond);
   if (c->d.world > 1) return fail(c, SPL_E_BADARG, "spl_apply_preconditioner needs world = 1");
@@ -2415,7 +2532,7 @@ int spl_apply_preconditioner(spl_ctx* c, const void* r, void* z, float* ms) {
 
 int spl_profile_pcg(spl_ctx* c, double dt, int iters, float* ms_a, float* ms_b, float* ms_x) {
   if (!c || !ms_a || !ms_b || !ms_x) return SPL_E_BADARG;
-  if (!c->uploaded) return fail(c, SPL_E_STATE, "spl_profile_pcg before spl_upload");
+  NEED_UPLOAD(c, "spl_profile_pcg");
   if (iters < 1 || iters > 256) return fail(c, SPL_E_BADARG, "iters must be in [1, 256]");
   if (!(dt > 0.0)) return fail(c, SPL_E_BADARG, "dt must be positive");
   CU(cudaSetDevice(c->d.device));

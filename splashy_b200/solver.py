@@ -291,3 +291,17 @@ class Solver:
     def download_ptrs(self, u_ptr, v_ptr, w_ptr, p_ptr, div_ptr=None):
         self._check(self._lib.spl_download(self._ctx, u_ptr, v_ptr, w_ptr,
                                            p_ptr, div_ptr))
+
+    # -- asynchronous transfers (pinned host buffers): spl_upload_async / spl_download_async --
+    def upload_async_ptrs(self, labels_ptr, u_ptr, v_ptr, w_ptr, p_ptr=None):
+        """Queue the host -> device copies and return; the next call that needs the state
+        waits for them on the device.  The buffers must stay untouched until then."""
+        self._check(self._lib.spl_upload_async(self._ctx, labels_ptr, u_ptr, v_ptr,
+                                               w_ptr, p_ptr))
+
+    def download_async_ptrs(self, u_ptr, v_ptr, w_ptr, p_ptr):
+        """Queue the device -> host copies; `sync()` waits for them."""
+        self._check(self._lib.spl_download_async(self._ctx, u_ptr, v_ptr, w_ptr, p_ptr))
+
+    def sync(self):
+        self._check(self._lib.spl_sync(self._ctx))

@@ -62,7 +62,7 @@ def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=
                 s1.set_fixed_iters(fixed)
             info1 = s1.step(dt)
             one = s1.download()
-        vs = max(np.abs(one[k]).max() for k in "UVW")
+        vs = float(max(np.abs(one[k]).max() for k in "UVW"))
         err_one = max(float(np.abs(out[k] - one[k]).max()) for k in "UVW") / vs
         # the numpy oracle on the whole box: only while it finishes in seconds (at 8 slabs the
         # larger cases are compared with the one-GPU run alone, itself oracle-checked by pytest)
@@ -132,7 +132,7 @@ def main():
     ok = True
     if rank == 0:
         ok = all(r["ok"] for r in results)
-        print(json.dumps({"mgpu_check": "ok" if ok else "FAILED", "results": results}))
+        print(json.dumps({"mgpu_check": "ok" if ok else "FAILED", "results": results}, default=float))
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

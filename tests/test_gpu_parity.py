@@ -839,6 +839,55 @@ def test_rbic0_quad_sweeps_equal_the_one_cell_sweeps(shape, monkeypatch):
         assert np.abs(got[n] - r).max() <= 5e-4 * vscale(U2, V2, W2), n
 
 
+def test_async_transfers_and_two_boxes_in_flight_match_the_blocking_calls():
+    """spl_upload_async / spl_download_async / spl_sync (pinned buffers): the same bytes as
+    spl_upload / spl_step / spl_download, also with two contexts interleaved the way bench.py's
+    end-to-end leg does it, and with a state error when nothing was uploaded."""
+    import ctypes as C
+    from splashy_b200 import PinnedArray
+    sc = scenes.vortex(64, 40, 24, dtype=np.float32)
+    lab, U, V, W = fields(sc, np.float32)
+    shape = lab.shape
+    ptr = lambda a: C.c_void_p(a.array.ctypes.data)
+    hin = {k: PinnedArray(shape, np.float32) for k in "UVW"}
+    hlab = PinnedArray(shape, np.uint8)
+    hlab.array[...] = lab
+    for k, a in zip("UVW", (U, V, W)):
+        hin[k].array[...] = a
+    outs = [{k: PinnedArray(shape, np.float32) for k in "UVWP"} for _ in range(2)]
+    with solver_for(sc, dtype=np.float32) as s:
+        s.upload(lab, U, V, W)
+        s.set_fixed_iters(30)
+        s.step(sc["dt"])
+        want = s.download()
+    with solver_for(sc, dtype=np.float32) as a, solver_for(sc, dtype=np.float32) as b:
+        with pytest.raises(SplashyError):
+            a.step(sc["dt"])                                  # nothing uploaded yet
+        boxes = [a, b]
+        for x in boxes:
+            x.set_fixed_iters(30)
+        up = lambda x: x.upload_async_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
+        up(a)
+        for i in range(5):
+            x, out = boxes[i % 2], outs[i % 2]
+            if i + 1 < 5:
+                up(boxes[(i + 1) % 2])
+            info = x.step(sc["dt"])
+            assert info["iters"] == 30
+            x.download_async_ptrs(ptr(out["U"]), ptr(out["V"]), ptr(out["W"]), ptr(out["P"]))
+        for x in boxes:
+            x.sync()
+        for out in outs:
+            for n in "UVW":
+                assert np.array_equal(out[n].array, want[n]), n
+            assert np.array_equal(out["P"].array, want["P"].astype(np.float32))
+        # a blocking upload after asynchronous traffic, and a blocking download of a pending one
+        up(a)
+        got = a.download()
+        for n, r in (("U", U), ("V", V), ("W", W)):
+            assert np.array_equal(got[n], r), n
+
+
 # --------------------------------------------------------------------------
 # BASELINE sizes: size-independent properties
 # --------------------------------------------------------------------------
