@@ -149,6 +149,81 @@ __global__ void k_peer_gather(PeerPtrs peers, int rank, int world, unsigned long
   }
 }
 
+// ---- halo planes over peer memory: the mailbox exchange (world > 1) ---------------------------
+// Every rank owns one IPC-shared mailbox: a header of sequence words and, per side (the
+// neighbour below / above) two data slots.  An exchange of boundary planes is ONE launch:
+//   sender CTAs    store this rank's bottom planes into the lower neighbour's mailbox and its
+//                  top planes into the upper neighbour's (NVLink stores), one system-scope fence
+//                  per CTA, and the last of them releases the exchange's sequence number into the
+//                  neighbours' headers;
+//   receiver CTAs  wait (bounded) for the neighbours' sequence number in the OWN header -- local
+//                  memory -- and copy the slots into the halo planes.
+// Senders never wait, and both kinds are resident together (<= 2 x 48 CTAs), so no rank depends
+// on a launch its own stream has not issued.  Every rank issues the same exchanges in the same
+// order on its compute stream; a neighbour can be at most one exchange ahead (it needs this
+// rank's planes for the next one), hence two slots indexed by the parity of the sequence number.
+// Works for any field of any multigrid level and any element size: the mailbox is the only
+// mapped buffer.  An alternative to ncclSend / ncclRecv in exchange_halo / exchange_level, opt-in
+// with SPL_MAILBOX=1 (see map_mailboxes: measured, not faster than NCCL on NVLink 5).
+struct alignas(256) MailHdr {
+  unsigned long long seq[2][2];      // [side][slot]: the exchange whose planes are complete
+};
+struct MailArgs {
+  const char* src[2];                // my planes for the neighbour below / above
+  char* dst[2];                      // its mailbox slot (mapped), nullptr = no neighbour
+  unsigned long long* dst_seq[2];
+  const char* slot[2];               // my mailbox slot filled by the neighbour below / above
+  const unsigned long long* my_seq[2];
+  char* halo[2];                     // my halo planes below / above
+  size_t bytes;
+  unsigned long long seq;
+  int unit;                          // bytes per access: 16, 8, 4 or 1
+};
+
+template <typename V>
+__device__ __forceinline__ void mail_copy(char* dst, const char* src, size_t bytes, int part,
+                                          int parts, bool cg) {
+  const size_t n = bytes / sizeof(V);
+  V* d = reinterpret_cast<V*>(dst);
+  const V* s = reinterpret_cast<const V*>(src);
+  for (size_t i = (size_t)part * blockDim.x + threadIdx.x; i < n; i += (size_t)parts * blockDim.x)
+    d[i] = cg ? __ldcg(s + i) : s[i];
+}
+__device__ __forceinline__ void mail_copy_any(char* dst, const char* src, size_t bytes, int unit,
+                                              int part, int parts, bool cg) {
+  if (unit == 16) mail_copy<uint4>(dst, src, bytes, part, parts, cg);
+  else if (unit == 8) mail_copy<unsigned long long>(dst, src, bytes, part, parts, cg);
+  else if (unit == 4) mail_copy<unsigned>(dst, src, bytes, part, parts, cg);
+  else mail_copy<unsigned char>(dst, src, bytes, part, parts, cg);
+}
+
+__global__ void __launch_bounds__(256)
+k_mail_exchange(MailArgs a, unsigned* ticket, int nsend) {
+  if ((int)blockIdx.x < nsend) {
+    for (int side = 0; side < 2; ++side)
+      if (a.dst[side]) mail_copy_any(a.dst[side], a.src[side], a.bytes, a.unit, blockIdx.x, nsend, false);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const unsigned t = atomicAdd(ticket, 1u);
+      if (t == (unsigned)nsend - 1u) {
+        *ticket = 0u;
+        __threadfence_system();
+        for (int side = 0; side < 2; ++side)
+          if (a.dst[side]) st_release_sys(a.dst_seq[side], a.seq);
+      }
+    }
+  } else {
+    const int part = (int)blockIdx.x - nsend, parts = (int)gridDim.x - nsend;
+    if (threadIdx.x == 0)
+      for (int side = 0; side < 2; ++side)
+        if (a.my_seq[side]) spin_until(a.my_seq[side], a.seq);
+    __syncthreads();
+    for (int side = 0; side < 2; ++side)
+      if (a.my_seq[side]) mail_copy_any(a.halo[side], a.slot[side], a.bytes, a.unit, part, parts, true);
+  }
+}
+
 struct MgLevel {
   Geo g{};
   uint8_t *media = nullptr, *codes = nullptr;   // plane-0 pointers
@@ -208,6 +283,13 @@ struct spl_ctx {
   void* peer_maps[MAXW]{};     // IPC mappings to close
   char* nb_sbuf[2][MAX_SBUF]{};   // the neighbours' (below / above) direction buffers, allocation starts
   void* nb_maps[2][MAX_SBUF]{};
+  // mailbox exchange of halo planes (k_mail_exchange)
+  char* mbox = nullptr;           // own mailbox: MailHdr + 2 sides x 2 slots
+  size_t mbox_slot = 0;           // bytes per slot
+  char* nb_mbox[2]{};             // the neighbours' mailboxes (below / above), IPC-mapped
+  unsigned long long xseq = 0;    // exchanges issued so far
+  unsigned* xticket = nullptr;
+  bool mbox_ok = false;
   bool fused_ok = false;       // the PCG iteration runs over peer memory (SPL_FUSED=0: separate gathers)
   unsigned long long pseq = 0;
   unsigned long long iter_seq = 0;
@@ -338,6 +420,55 @@ ncclDataType_t nccl_real(const spl_ctx* c) {
   return c->d.dtype == SPL_F64 ? ncclDouble : ncclFloat;
 }
 
+// boundary planes through the mailboxes: `lo_src` / `hi_src` = this rank's bottom / top planes,
+// `lo_halo` / `hi_halo` = where the neighbours' planes belong, `bytes` each
+static int gcd_align(size_t x) { return (x % 16 == 0) ? 16 : (x % 8 == 0) ? 8 : (x % 4 == 0) ? 4 : 1; }
+int mail_exchange(spl_ctx* c, const char* lo_src, const char* hi_src, char* lo_halo, char* hi_halo,
+                  size_t bytes) {
+  const int rank = c->d.rank, world = c->d.world;
+  const unsigned long long seq = ++c->xseq;
+  const int sl = (int)(seq & 1ull);
+  MailArgs a{};
+  a.bytes = bytes;
+  a.seq = seq;
+  auto slot_of = [&](char* box, int side) {
+    return box + sizeof(MailHdr) + ((size_t)side * 2 + sl) * c->mbox_slot;
+  };
+  auto seq_of = [&](char* box, int side) { return &reinterpret_cast<MailHdr*>(box)->seq[side][sl]; };
+  int unit = gcd_align(bytes);
+  auto fold = [&](const void* p) {
+    const int al = gcd_align((size_t)reinterpret_cast<uintptr_t>(p));
+    if (al < unit) unit = al;
+  };
+  if (rank > 0) {                       // I am the lower neighbour's "above" side (1)
+    a.src[0] = lo_src;
+    a.dst[0] = slot_of(c->nb_mbox[0], 1);
+    a.dst_seq[0] = seq_of(c->nb_mbox[0], 1);
+    a.slot[0] = slot_of(c->mbox, 0);
+    a.my_seq[0] = seq_of(c->mbox, 0);
+    a.halo[0] = lo_halo;
+    fold(lo_src); fold(lo_halo);
+  }
+  if (rank < world - 1) {
+    a.src[1] = hi_src;
+    a.dst[1] = slot_of(c->nb_mbox[1], 0);
+    a.dst_seq[1] = seq_of(c->nb_mbox[1], 0);
+    a.slot[1] = slot_of(c->mbox, 1);
+    a.my_seq[1] = seq_of(c->mbox, 1);
+    a.halo[1] = hi_halo;
+    fold(hi_src); fold(hi_halo);
+  }
+  a.unit = unit;
+  // one sender + one receiver CTA per 64 KiB, at most 48 + 48 (all resident at once)
+  int n = (int)((bytes + 65535) / 65536);
+  if (n < 1) n = 1;
+  if (n > 48) n = 48;
+  k_mail_exchange<<<2 * n, 256, 0, c->stream>>>(a, c->xticket, n);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SPL_OK;
+}
+
 // exchange `width` z-planes of a field with both slab neighbours
 int exchange_halo(spl_ctx* c, char* plane0, size_t es, ncclDataType_t ty, int width,
                   cudaStream_t st = nullptr) {
@@ -348,6 +479,9 @@ int exchange_halo(spl_ctx* c, char* plane0, size_t es, ncclDataType_t ty, int wi
   if (width > g.nz) width = g.nz;
   const size_t cnt = (size_t)g.plane * width;
   const size_t pb = (size_t)g.plane * es;
+  if (c->mbox_ok && st == c->stream && cnt * es <= c->mbox_slot)
+    return mail_exchange(c, plane0, plane0 + (size_t)(g.nz - width) * pb,
+                         plane0 - (size_t)width * pb, plane0 + (size_t)g.nz * pb, cnt * es);
   NC(g_nccl.GroupStart());
   if (c->d.rank > 0) {
     NC(g_nccl.Send(plane0, cnt, ty, c->d.rank - 1, c->comm, st));
@@ -368,6 +502,9 @@ int exchange_level(spl_ctx* c, const Geo& g, void* plane0_, size_t es, ncclDataT
   char* plane0 = static_cast<char*>(plane0_);
   const size_t cnt = (size_t)g.plane;
   const size_t pb = cnt * es;
+  if (c->mbox_ok && pb <= c->mbox_slot)
+    return mail_exchange(c, plane0, plane0 + (size_t)(g.nz - 1) * pb, plane0 - pb,
+                         plane0 + (size_t)g.nz * pb, pb);
   NC(g_nccl.GroupStart());
   if (c->d.rank > 0) {
     NC(g_nccl.Send(plane0, cnt, ty, c->d.rank - 1, c->comm, c->stream));
@@ -1441,6 +1578,10 @@ void spl_destroy(spl_ctx* c) {
   for (int side = 0; side < 2; ++side)
     for (int i = 0; i < MAX_SBUF; ++i)
       if (c->nb_maps[side][i]) cudaIpcCloseMemHandle(c->nb_maps[side][i]);
+  for (int side = 0; side < 2; ++side)
+    if (c->nb_mbox[side]) cudaIpcCloseMemHandle(c->nb_mbox[side]);
+  if (c->mbox) cudaFree(c->mbox);
+  if (c->xticket) cudaFree(c->xticket);
   if (c->pbox) cudaFree(c->pbox);
   if (c->hticket) cudaFree(c->hticket);
   if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
@@ -1529,6 +1670,62 @@ static int map_neighbour_sbufs(spl_ctx* c) {
   CU(cudaStreamSynchronize(c->stream));
   for (int w = 0; w < d.world; ++w) ok = ok && hh[w];
   c->fused_ok = ok;
+  CU(cudaFree(dh));
+  return SPL_OK;
+}
+
+// the mailboxes of k_mail_exchange: allocate, exchange the IPC handles through NCCL, map the two
+// neighbours'; used only if every rank mapped what it needs (SPL_MAILBOX=0: ncclSend / ncclRecv)
+static int map_mailboxes(spl_ctx* c) {
+  const spl_desc& d = c->d;
+  // Opt-in (SPL_MAILBOX=1): measured on 2 B200s with the multigrid step at 512^3 per GPU
+  // (28 plane exchanges per V-cycle) it is no faster than NCCL's grouped send / recv -- 42.3 ms
+  // against 41.5 ms per 14 iterations, profiles/README.md round 2 -- so NCCL stays the default.
+  const char* me = getenv("SPL_MAILBOX");
+  bool ok = c->p2p && me && atoi(me) != 0;
+  // a slot holds the widest exchange: hz planes of a velocity component or one fp64 plane
+  size_t slot = (size_t)c->g.plane * (size_t)std::max<size_t>((size_t)c->g.hz * c->esz, 8);
+  slot = (slot + 255) / 256 * 256;
+  c->mbox_slot = slot;
+  const size_t total = sizeof(MailHdr) + 4 * slot;
+  if (ok && cudaMalloc(&c->mbox, total) != cudaSuccess) { cudaGetLastError(); c->mbox = nullptr; ok = false; }
+  if (ok) CU(cudaMemsetAsync(c->mbox, 0, sizeof(MailHdr), c->stream));
+  CU(cudaMalloc(&c->xticket, sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->xticket, 0, sizeof(unsigned), c->stream));
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  if (ok && cudaIpcGetMemHandle(&mine, c->mbox) != cudaSuccess) { cudaGetLastError(); ok = false; }
+  std::vector<unsigned char> hh((size_t)65 * d.world, 0);
+  unsigned char* dh = nullptr;
+  CU(cudaMalloc(&dh, hh.size()));
+  memcpy(&hh[(size_t)65 * d.rank], &mine, 64);
+  hh[(size_t)65 * d.rank + 64] = ok;
+  CU(cudaMemcpyAsync(dh + (size_t)65 * d.rank, &hh[(size_t)65 * d.rank], 65, cudaMemcpyHostToDevice,
+                     c->stream));
+  NC(g_nccl.AllGather(dh + (size_t)65 * d.rank, dh, 65, ncclUint8, c->comm, c->stream));
+  CU(cudaMemcpyAsync(hh.data(), dh, hh.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int w = 0; w < d.world; ++w) ok = ok && hh[(size_t)65 * w + 64];
+  for (int side = 0; side < 2 && ok; ++side) {
+    const int nb = side == 0 ? d.rank - 1 : d.rank + 1;
+    if (nb < 0 || nb >= d.world) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, &hh[(size_t)65 * nb], 64);
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;
+      break;
+    }
+    c->nb_mbox[side] = static_cast<char*>(ptr);
+  }
+  unsigned char mapped = ok;           // agree: all ranks or none
+  CU(cudaMemcpyAsync(dh + d.rank, &mapped, 1, cudaMemcpyHostToDevice, c->stream));
+  NC(g_nccl.AllGather(dh + d.rank, dh, 1, ncclUint8, c->comm, c->stream));
+  CU(cudaMemcpyAsync(hh.data(), dh, d.world, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int w = 0; w < d.world; ++w) ok = ok && hh[w];
+  c->mbox_ok = ok;
   CU(cudaFree(dh));
   return SPL_OK;
 }
@@ -1698,6 +1895,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   for (int i = 0; i < c->nsbuf; ++i)
     if ((rc = alloc_field(c, 32 + i, c->esz, &c->sbuf[i], 0))) return rc;
   if (d.world > 1 && (rc = map_neighbour_sbufs(c))) return rc;
+  if (d.world > 1 && (rc = map_mailboxes(c))) return rc;
   if (d.precond == SPL_PC_RBIC0 || d.precond == SPL_PC_MG) {
     if ((rc = alloc_field(c, 11, c->esz, &c->z, 0))) return rc;
     if ((rc = alloc_field(c, 12, c->esz, &c->einv, 0))) return rc;
