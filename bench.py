@@ -443,14 +443,21 @@ def run_cuda(args):
         boxes = [(s, hout), (s2, hout2)]
         up = lambda b: b.upload_async_ptrs(ptr(hlab), ptr(hin["U"]), ptr(hin["V"]), ptr(hin["W"]))
 
+        per_box = [[], []]
+
         def run(n):
             dev = 0.0
+            per_box[0].clear(); per_box[1].clear()
             up(boxes[0][0])
+            boxes[0][0].sync()          # pipeline fill: the first upload has the link to itself
             for i in range(n):
                 b, out = boxes[i % 2]
                 if i + 1 < n:
                     up(boxes[(i + 1) % 2][0])
-                dev += b.step(dt)["ms_total"]
+                info_ = b.step(dt)
+                dev += info_["ms_total"]
+                per_box[i % 2].append({k: round(info_[k], 2) for k in
+                                       ("ms_total", "ms_advect", "ms_rhs", "ms_solve", "ms_grad")})
                 b.download_async_ptrs(ptr(out["U"]), ptr(out["V"]), ptr(out["W"]), ptr(out["P"]))
             for b, _ in boxes:
                 b.sync()
@@ -624,6 +631,8 @@ def run_cuda(args):
                     "result_checksum": checksum, "mode": e2e_mode,
                     "same_result_as_one_box": e2e_match,
                     "step_device_ms": e2e_step_dev_ms,
+                    "last_steps_per_box": [pb[-1] if pb else None for pb in per_box]
+                    if e2e_step_dev_ms else None,
                     "one_box": {"value": cells / e2e_one_s, "ms_per_step": e2e_one_s * 1e3,
                                 "mode": "upload, step, download of ONE box in sequence"},
                     "pinned_numa_node": numa[0] if numa else None},

@@ -263,6 +263,10 @@ struct spl_ctx {
   int* hdone = nullptr;        // pinned [2]: lagged convergence poll
   double* hagree = nullptr;    // pinned [MAXW + 1]: agree_max
   cudaEvent_t dev[2]{};
+  // device aliases of the mapped pinned scalars below (to_host / from_host)
+  Scal* hsc_d = nullptr;
+  int *hflag_d = nullptr, *hdone_d = nullptr;
+  unsigned long long *hesc = nullptr, *hesc_d = nullptr;   // trace escapes of the last advection
   ncclComm_t comm = nullptr;
   // z-slabs: the direction halo travels on a second (high-priority) stream while the interior
   // chunks of phase A run (SPL_OVERLAP=0: everything on one stream); the per-rank CG scalars
@@ -557,8 +561,32 @@ int agree_max(spl_ctx* c, double v, double* out) {
   return SPL_OK;
 }
 
+// Scalars between host and device travel as a one-block kernel through MAPPED pinned memory,
+// not as cudaMemcpyAsync: a copy of a few bytes queues on the copy engine behind whatever bulk
+// transfer another stream has in flight (spl_upload_async / spl_download_async of a second box:
+// 512 MiB pieces, ~10 ms each) and the compute stream would wait for it -- measured: 27 ms per
+// step in bench.py's two-box end-to-end leg before this change.
+__global__ void k_copy_words(unsigned* __restrict__ dst, const unsigned* __restrict__ src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+// bytes % 4 == 0; `host_dev` = the device alias of a mapped pinned buffer
+static int to_host(spl_ctx* c, void* host_dev, const void* dev, size_t bytes) {
+  k_copy_words<<<1, 256, 0, c->stream>>>(static_cast<unsigned*>(host_dev),
+                                        static_cast<const unsigned*>(dev), (int)(bytes / 4));
+  CU(cudaGetLastError());
+  return SPL_OK;
+}
+static int from_host(spl_ctx* c, void* dev, const void* host_dev, size_t bytes) {
+  k_copy_words<<<1, 256, 0, c->stream>>>(static_cast<unsigned*>(dev),
+                                        static_cast<const unsigned*>(host_dev), (int)(bytes / 4));
+  CU(cudaGetLastError());
+  return SPL_OK;
+}
+
 int pull_scal(spl_ctx* c) {
-  CU(cudaMemcpyAsync(c->hsc, c->sc, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream));
+  int rc = to_host(c, c->hsc_d, c->sc, sizeof(Scal));
+  if (rc) return rc;
   CU(cudaStreamSynchronize(c->stream));
   return SPL_OK;
 }
@@ -1216,7 +1244,8 @@ struct Impl {
     h->nonfinite = keep_nf;
     for (int w = 0; w < c->d.world; ++w)
       h->gBM[1][w][0] = (w == 0) ? std::numeric_limits<double>::infinity() : 0.0;
-    CU(cudaMemcpyAsync(c->sc, h, sizeof(Scal), cudaMemcpyHostToDevice, c->stream));
+    static_assert(sizeof(Scal) % 4 == 0, "Scal is copied in 32-bit words");
+    if (int rc_ = from_host(c, c->sc, c->hsc_d, sizeof(Scal))) return rc_;
     CU(cudaStreamSynchronize(c->stream));   // h is reused below
 
     const int gridB = grid_for(c, g.ncell / VEC);
@@ -1355,8 +1384,7 @@ struct Impl {
       // lagged poll: the flag of batch b is read while batch b+1 is already queued, so
       // the GPU never waits for the host (a converged solve only runs no-op launches)
       const int slot = batch & 1;
-      CU(cudaMemcpyAsync(&c->hdone[slot], &c->sc->done, sizeof(int), cudaMemcpyDeviceToHost,
-                         c->stream));
+      if (int rc_ = to_host(c, &c->hdone_d[slot], &c->sc->done, sizeof(int))) return rc_;
       CU(cudaEventRecord(c->dev[slot], c->stream));
       if (batch >= 1) {
         CU(cudaEventSynchronize(c->dev[slot ^ 1]));
@@ -1611,6 +1639,7 @@ void spl_destroy(spl_ctx* c) {
   if (c->hsc) cudaFreeHost(c->hsc);
   if (c->hflag) cudaFreeHost(c->hflag);
   if (c->hdone) cudaFreeHost(c->hdone);
+  if (c->hesc) cudaFreeHost(c->hesc);
   if (c->hagree) cudaFreeHost(c->hagree);
   for (cudaEvent_t e : c->dev)
     if (e) cudaEventDestroy(e);
@@ -1994,9 +2023,16 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   CU(cudaMemsetAsync(c->sc, 0, sizeof(Scal), c->stream));
   CU(cudaMalloc(&c->partials, sizeof(double) * 2 * MAX_PARTIALS));
   CU(cudaMalloc(&c->flag, sizeof(int)));
-  CU(cudaHostAlloc(&c->hsc, sizeof(Scal), cudaHostAllocDefault));
-  CU(cudaHostAlloc(&c->hflag, sizeof(int), cudaHostAllocDefault));
-  CU(cudaHostAlloc(&c->hdone, 2 * sizeof(int), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&c->hsc, sizeof(Scal), cudaHostAllocMapped));
+  CU(cudaHostAlloc(&c->hflag, sizeof(int), cudaHostAllocMapped));
+  CU(cudaHostAlloc(&c->hdone, 2 * sizeof(int), cudaHostAllocMapped));
+  CU(cudaHostAlloc(&c->hesc, sizeof(unsigned long long), cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hsc_d), c->hsc, 0));
+  CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hflag_d), c->hflag, 0));
+  CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hdone_d), c->hdone, 0));
+  CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->hesc_d), c->hesc, 0));
+  *c->hesc = 0;
+  *c->hflag = 0;
   CU(cudaHostAlloc(&c->hagree, (MAXW + 1) * sizeof(double), cudaHostAllocDefault));
   for (auto& e : c->dev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
@@ -2214,7 +2250,7 @@ int spl_advect(spl_ctx* c, double dt, spl_info* info) {
   int rc = DISPATCH(c, Impl<float>::advect(c, dt), Impl<double>::advect(c, dt));
   if (rc) return rc;
   CU(cudaEventRecord(c->ev[1], c->stream));
-  CU(cudaMemcpyAsync(c->hflag, c->flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = to_host(c, c->hflag_d, c->flag, sizeof(int)))) return rc;
   if ((rc = pull_scal(c))) return rc;
   c->have_rhs = false;
   if (info) {
@@ -2327,21 +2363,14 @@ static int project_impl(spl_ctx* c, double dt, spl_info* info, bool with_advect)
   CU(cudaEventRecord(c->ev[0], c->stream));
   if (with_advect) {
     if ((rc = DISPATCH(c, Impl<float>::advect(c, dt), Impl<double>::advect(c, dt)))) return rc;
-    // escapes are read back with the scalars below; keep them across the pcg reset
-    CU(cudaMemcpyAsync(&c->hsc->escapes, &c->sc->escapes, sizeof(unsigned long long),
-                       cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->hflag, c->flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    // the escape counter and the quirk flag leave the device now (the solve resets the scalar
+    // block) but are only looked at after the step: no host round trip between the stages
+    if ((rc = to_host(c, c->hesc_d, &c->sc->escapes, sizeof(unsigned long long)))) return rc;
+    if ((rc = to_host(c, c->hflag_d, c->flag, sizeof(int)))) return rc;
   }
   CU(cudaEventRecord(c->ev[1], c->stream));
   if ((rc = do_rhs(c, dt))) return rc;
   CU(cudaEventRecord(c->ev[2], c->stream));
-  unsigned long long escapes = 0;
-  int too_far = 0;
-  if (with_advect) {
-    CU(cudaStreamSynchronize(c->stream));
-    escapes = c->hsc->escapes;
-    too_far = c->d.quirks ? *c->hflag : 0;
-  }
   c->iters_base = 0;
   // with a refinement round to follow, the first pass only needs to reach the level where
   // the fp32 recursive residual stops tracking the true one (~1e-4 max|b| on large grids);
@@ -2388,7 +2417,9 @@ static int project_impl(spl_ctx* c, double dt, spl_info* info, bool with_advect)
   CU(cudaEventRecord(c->ev[5], c->stream));
   spl_info local;
   memset(&local, 0, sizeof local);
-  if ((rc = read_back(c, &local, true, true))) return rc;
+  if ((rc = read_back(c, &local, true, true))) return rc;      // synchronises the stream
+  const unsigned long long escapes = with_advect ? *c->hesc : 0ull;
+  const int too_far = (with_advect && c->d.quirks) ? *c->hflag : 0;
   local.trace_escapes = (int64_t)escapes;
   local.ms_advect = ev_ms(c, 0, 1);
   local.ms_rhs = ev_ms(c, 1, 2);
