@@ -197,7 +197,9 @@ void  spl_host_free(void* p);
 /* ---- marker stage: the step before the path ---------------------
  * Simulator.fs:19-52,60-79.  Markers are fp64 locations in metres held on the device;
  * cell of a location = Coord.construct(float) (Coord.fs:49-67) minus desc.origin.
- * world = 1 only.                                                               */
+ * z-slabs (world > 1): every rank passes and holds ALL markers; a marker is moved by the
+ * rank whose slab holds its cell and one all-reduce hands every rank the new locations;
+ * bounds (spl_set_world) are box indices of the GLOBAL box.  SPL_Q_MOVE_CELLS: world = 1. */
 /* World.contains (World.fs:11-14, Aabb.fs:13-17) as inclusive box-index bounds; cells
  * created outside become Solid (Build.fs:95-98).  Default: the whole box.          */
 int  spl_set_world(spl_ctx* ctx, const int lo[3], const int hi[3]);

@@ -49,6 +49,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t,
                        cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t,
@@ -79,6 +81,7 @@ bool load_nccl(std::string& err) {
   SPL_SYM(CommInitRank, "ncclCommInitRank")
   SPL_SYM(CommDestroy, "ncclCommDestroy")
   SPL_SYM(AllGather, "ncclAllGather")
+  SPL_SYM(AllReduce, "ncclAllReduce")
   SPL_SYM(Send, "ncclSend")
   SPL_SYM(Recv, "ncclRecv")
   SPL_SYM(GroupStart, "ncclGroupStart")
@@ -313,7 +316,8 @@ struct spl_ctx {
   long long nmark = 0;
   double* mloc = nullptr;      // nmark x 3 locations (metres)
   long long *mold = nullptr, *mnew = nullptr;   // cells before / after the last move
-  uint8_t* mark = nullptr;     // per cell: holds a marker / existed before relabelling
+  uint8_t* mark = nullptr;     // per cell: holds a marker / existed before relabelling (plane 0)
+  void* mark_base = nullptr;   // its allocation (z-halo planes included)
   MarkerStats* mstats = nullptr;   // device
   WorldBox world{};            // World.contains as box indices
   std::vector<MgLevel> mg;     // SPL_PC_MG hierarchy; level 0 aliases codes / z / r / q
@@ -1498,6 +1502,8 @@ struct Impl {
       if (rc_) return rc_;                                                         \
     }                                                                              \
     if (!(c)->uploaded) return fail(c, SPL_E_STATE, who " before spl_upload");     \
+    /* a queued spl_download_async still reads the fields: later work waits for it */ \
+    if ((c)->download_queued) cudaStreamWaitEvent((c)->stream, (c)->ev_down, 0);   \
   } while (0)
 
 #define DISPATCH(c, expr_f32, expr_f64) ((c)->d.dtype == SPL_F64 ? (expr_f64) : (expr_f32))
@@ -1631,7 +1637,7 @@ void spl_destroy(spl_ctx* c) {
   if (c->mloc) cudaFree(c->mloc);
   if (c->mold) cudaFree(c->mold);
   if (c->mnew) cudaFree(c->mnew);
-  if (c->mark) cudaFree(c->mark);
+  if (c->mark_base) cudaFree(c->mark_base);
   if (c->mstats) cudaFree(c->mstats);
   if (c->sc) cudaFree(c->sc);
   if (c->partials) cudaFree(c->partials);
@@ -2038,7 +2044,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
 
   c->d.nccl_id = nullptr;   // caller-owned bytes are not kept
   for (int a = 0; a < 3; ++a) c->world.lo[a] = 0;
-  c->world.hi[0] = c->g.nx - 1; c->world.hi[1] = c->g.ny - 1; c->world.hi[2] = c->g.nz - 1;
+  c->world.hi[0] = c->g.nx - 1; c->world.hi[1] = c->g.ny - 1; c->world.hi[2] = c->g.nzg - 1;
   CU(cudaStreamSynchronize(c->stream));
   return SPL_OK;
 }
@@ -2462,11 +2468,17 @@ static int markers_need(spl_ctx* c, const char* who) {
   if (!integral_h(c))   // Coord.nearest works on int<m> (Coord.fs:49-57, Constants.fs:11 h = 10)
     return fail(c, SPL_E_BADARG, "%s: the marker stage needs an integral cell size h >= 1", who);
   if (c->nmark <= 0) return fail(c, SPL_E_STATE, "%s before spl_set_markers", who);
-  if (c->d.world > 1) return fail(c, SPL_E_BADARG, "the marker stage needs world = 1");
+  if (c->d.world > 1 && (c->d.quirks & SPL_Q_MOVE_CELLS))   // a record would have to change rank
+    return fail(c, SPL_E_BADARG, "%s: SPL_Q_MOVE_CELLS needs world = 1", who);
   return SPL_OK;
 }
 
+// the counters of the marker kernels, summed over the ranks: every rank takes the same
+// decision (an error that one rank alone acted on would leave the others in a collective)
 static int read_marker_stats(spl_ctx* c, MarkerStats* out) {
+  static_assert(sizeof(MarkerStats) == 3 * sizeof(unsigned long long), "three counters");
+  if (c->d.world > 1)
+    NC(g_nccl.AllReduce(c->mstats, c->mstats, 3, ncclUint64, ncclSum, c->comm, c->stream));
   CU(cudaMemcpyAsync(out, c->mstats, sizeof(MarkerStats), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return SPL_OK;
@@ -2483,7 +2495,6 @@ int spl_set_world(spl_ctx* c, const int lo[3], const int hi[3]) {
 
 int spl_set_markers(spl_ctx* c, int64_t n, const double* xyz) {
   if (!c || n < 0 || (n > 0 && !xyz)) return SPL_E_BADARG;
-  if (c->d.world > 1) return fail(c, SPL_E_BADARG, "the marker stage needs world = 1");
   if (!integral_h(c))
     return fail(c, SPL_E_BADARG, "spl_set_markers: the marker stage needs an integral cell size h >= 1");
   CU(cudaSetDevice(c->d.device));
@@ -2491,7 +2502,11 @@ int spl_set_markers(spl_ctx* c, int64_t n, const double* xyz) {
   c->mloc = nullptr; c->mold = c->mnew = nullptr;
   c->nmark = n;
   if (!c->mstats) CU(cudaMalloc(&c->mstats, sizeof(MarkerStats)));
-  if (!c->mark) CU(cudaMalloc(&c->mark, (size_t)c->g.ncell));
+  if (!c->mark) {   // allocated like a field: the relabelling reads the neighbour slab's plane
+    CU(cudaMalloc(&c->mark_base, field_bytes(c, 1)));
+    CU(cudaMemsetAsync(c->mark_base, 0, field_bytes(c, 1), c->stream));
+    c->mark = static_cast<uint8_t*>(c->mark_base) + (size_t)c->g.hz * c->g.plane;
+  }
   if (n == 0) return SPL_OK;
   CU(cudaMalloc(&c->mloc, (size_t)n * 3 * sizeof(double)));
   CU(cudaMalloc(&c->mold, (size_t)n * sizeof(long long)));
@@ -2500,12 +2515,12 @@ int spl_set_markers(spl_ctx* c, int64_t n, const double* xyz) {
                      c->stream));
   CU(cudaMemsetAsync(c->mstats, 0, sizeof(MarkerStats), c->stream));
   LAUNCH(c, k_marker_cells, grid_for(c, n), 256, c->g, c->mloc, (long long)n, (int)c->d.h,
-         c->d.origin[0], c->d.origin[1], c->d.origin[2], c->mnew, c->mstats);
+         c->d.origin[0], c->d.origin[1], c->d.origin[2], c->mnew, c->mstats, 1);
   CU(cudaMemcpyAsync(c->mold, c->mnew, (size_t)n * sizeof(long long), cudaMemcpyDeviceToDevice,
                      c->stream));
-  MarkerStats st;
-  int rc = read_marker_stats(c, &st);
-  if (rc) return rc;
+  MarkerStats st;   // every rank holds every marker and counts the same ones: no reduction
+  CU(cudaMemcpyAsync(&st, c->mstats, sizeof(MarkerStats), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   if (st.outside)
     return fail(c, SPL_E_MARKER, "%llu marker(s) lie outside the dense box", st.outside);
   return SPL_OK;
@@ -2528,19 +2543,28 @@ int spl_move_markers(spl_ctx* c, double dt, int64_t* moved) {
   CU(cudaSetDevice(c->d.device));
   const long long n = c->nmark;
   const int sum_faces = (c->d.quirks & SPL_Q_MARKER_SUM) ? 1 : 0;
+  // a marker in plane 0 of a slab reads the -z face of the neighbour's top plane
+  if ((rc = exchange_velocity(c, 1))) return rc;
   CU(cudaMemsetAsync(c->mstats, 0, sizeof(MarkerStats), c->stream));
   if (c->d.dtype == SPL_F64) {
     LAUNCH(c, k_move_markers<double>, grid_for(c, n), 256, c->g, c->media,
            Impl<double>::P(c->u), Impl<double>::P(c->v), Impl<double>::P(c->w), c->mloc, n, dt,
            (int)c->d.h, c->d.origin[0], c->d.origin[1], c->d.origin[2], sum_faces, c->mold,
-           c->mnew, c->mstats);
+           c->mnew, c->mstats, c->d.rank, c->d.world);
   } else {
     LAUNCH(c, k_move_markers<float>, grid_for(c, n), 256, c->g, c->media, Impl<float>::P(c->u),
            Impl<float>::P(c->v), Impl<float>::P(c->w), c->mloc, n, dt, (int)c->d.h,
            c->d.origin[0], c->d.origin[1], c->d.origin[2], sum_faces, c->mold, c->mnew,
-           c->mstats);
+           c->mstats, c->d.rank, c->d.world);
   }
   CU(cudaGetLastError());
+  if (c->d.world > 1) {
+    // each location was written by exactly one rank (zeros elsewhere): the sum is exact
+    NC(g_nccl.AllReduce(c->mloc, c->mloc, (size_t)n * 3, ncclDouble, ncclSum, c->comm, c->stream));
+    LAUNCH(c, k_marker_cells, grid_for(c, n), 256, c->g, c->mloc, n, (int)c->d.h, c->d.origin[0],
+           c->d.origin[1], c->d.origin[2], c->mnew, c->mstats, 0);
+    CU(cudaGetLastError());
+  }
   MarkerStats st;
   if ((rc = read_marker_stats(c, &st))) return rc;
   if (moved) *moved = (int64_t)st.moved;
@@ -2573,8 +2597,13 @@ int spl_relabel(spl_ctx* c, int sanity) {
   CU(cudaMemsetAsync(c->mstats, 0, sizeof(MarkerStats), c->stream));
   LAUNCH(c, k_mark_cells, grid_for(c, c->nmark), 256, c->mnew, c->nmark, c->mark);
   LAUNCH(c, k_relabel_init, grid, 256, g, c->world, c->media, c->layer, c->mark, c->mstats);
-  for (int step = 1; step <= 2; ++step)   // Build.max_distance = max 2 (ceil time_step_constant)
+  for (int step = 1; step <= 2; ++step) {   // Build.max_distance = max 2 (ceil time_step_constant)
+    // slabs: the sources of a ring may sit in the neighbour's boundary plane
+    if ((rc = exchange_halo(c, reinterpret_cast<char*>(c->layer), 1, ncclUint8, 1))) return rc;
+    if ((rc = exchange_halo(c, reinterpret_cast<char*>(c->media), 1, ncclUint8, 1))) return rc;
+    if (lazy && (rc = exchange_halo(c, reinterpret_cast<char*>(c->mark), 1, ncclUint8, 1))) return rc;
     LAUNCH(c, k_relabel_step, grid, 256, g, c->world, c->media, c->layer, c->mark, step, lazy);
+  }
   double* p = reinterpret_cast<double*>(c->p);
   if (c->d.dtype == SPL_F64)
     LAUNCH(c, k_relabel_finish<double>, grid, 256, g, c->media, c->layer, c->mark,
@@ -2583,6 +2612,7 @@ int spl_relabel(spl_ctx* c, int sanity) {
     LAUNCH(c, k_relabel_finish<float>, grid, 256, g, c->media, c->layer, c->mark,
            Impl<float>::P(c->u), Impl<float>::P(c->v), Impl<float>::P(c->w), p);
   CU(cudaGetLastError());
+  if ((rc = exchange_halo(c, reinterpret_cast<char*>(c->media), 1, ncclUint8, g.hz))) return rc;
   if ((rc = rebuild_operators(c))) return rc;
   c->have_rhs = false;
   MarkerStats st;

@@ -6,7 +6,14 @@
 // keeps the grid in a Dictionary and edits it cell by cell; here the labels live in the
 // dense box, markers are an array of fp64 locations, and every stage is one data-parallel
 // pass (the BFS of the air buffer: max_distance = 2 passes).  Oracle:
-// oracle/dense_ref.py move_markers / move_cells / relabel.  world = 1 only.
+// oracle/dense_ref.py move_markers / move_cells / relabel.
+//
+// z-slabs (world > 1): every rank holds ALL marker locations.  A marker is moved by the rank
+// whose slab holds its cell (markers outside the global box: rank 0), the other ranks write
+// zeros, and one all-reduce (sum: exact, a single non-zero term) hands every rank the new
+// locations -- no migration, no variable-size messages.  The relabelling passes read the
+// neighbouring slab's boundary plane of the labels / layers through the z halo, exchanged
+// between the passes; bounds and the world test use the global plane index.
 #pragma once
 #include "spl_common.cuh"
 
@@ -28,12 +35,17 @@ __device__ __forceinline__ long long nearest_cell(double x, int h) {
   return s / h;
 }
 
+// local cell index of a location; MC_OUTSIDE = outside the (global) dense box, MC_REMOTE =
+// inside it but in another rank's slab.  (ox, oy, oz) = origin of the global box.
+constexpr long long MC_OUTSIDE = -1, MC_REMOTE = -2;
 __device__ __forceinline__ long long marker_cell(const Geo& g, const double* loc, int h,
                                                  int ox, int oy, int oz) {
   const long long i = nearest_cell(loc[0], h) - ox;
   const long long j = nearest_cell(loc[1], h) - oy;
-  const long long k = nearest_cell(loc[2], h) - oz;
-  if (i < 0 || j < 0 || k < 0 || i >= g.nx || j >= g.ny || k >= g.nz) return -1;
+  const long long kg = nearest_cell(loc[2], h) - oz;
+  if (i < 0 || j < 0 || kg < 0 || i >= g.nx || j >= g.ny || kg >= g.nzg) return MC_OUTSIDE;
+  const long long k = kg - g.z0;
+  if (k < 0 || k >= g.nz) return MC_REMOTE;
   return (k * g.ny + j) * g.nx + i;
 }
 
@@ -47,7 +59,8 @@ __global__ void k_move_markers(Geo g, const uint8_t* __restrict__ media,
                                const T* __restrict__ w, double* __restrict__ loc,
                                long long n, double dt, int h, int ox, int oy, int oz,
                                int sum_faces, long long* __restrict__ old_cell,
-                               long long* __restrict__ new_cell, MarkerStats* st) {
+                               long long* __restrict__ new_cell, MarkerStats* st, int rank,
+                               int world) {
   unsigned n_out = 0, n_moved = 0;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n;
        m += (long long)gridDim.x * blockDim.x) {
@@ -55,8 +68,12 @@ __global__ void k_move_markers(Geo g, const uint8_t* __restrict__ media,
     const long long idx = marker_cell(g, l, h, ox, oy, oz);
     old_cell[m] = idx;
     if (idx < 0) {
-      new_cell[m] = -1;
-      ++n_out;
+      // outside the box: stays where it is (rank 0 keeps and counts it); in another slab: its
+      // owner moves it.  Ranks that do not own a marker contribute zeros to the all-reduce.
+      new_cell[m] = idx;
+      if (idx == MC_OUTSIDE && rank == 0) ++n_out;
+      if (world > 1 && !(idx == MC_OUTSIDE && rank == 0))
+        loc[3 * m] = loc[3 * m + 1] = loc[3 * m + 2] = 0.0;
       continue;
     }
     const int i = (int)(idx % g.nx);
@@ -65,7 +82,7 @@ __global__ void k_move_markers(Geo g, const uint8_t* __restrict__ media,
     const int k = (int)(t / g.ny);
     const T* f[3] = {u, v, w};
     const long long off[3] = {1, (long long)g.nx, g.plane};
-    const bool inm[3] = {i > 0, j > 0, k > 0};
+    const bool inm[3] = {i > 0, j > 0, k + g.z0 > 0};   // plane -1 of a slab: the z halo
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       double vel = (double)f[a][idx];
@@ -76,8 +93,8 @@ __global__ void k_move_markers(Geo g, const uint8_t* __restrict__ media,
     }
     const long long nidx = marker_cell(g, l, h, ox, oy, oz);
     new_cell[m] = nidx;
-    n_out += (nidx < 0);
-    n_moved += (nidx >= 0 && nidx != idx);
+    n_out += (nidx == MC_OUTSIDE);
+    n_moved += (nidx != MC_OUTSIDE && nidx != idx);
   }
   // one atomic per warp (millions of markers move every step)
   n_out = __reduce_add_sync(0xffffffffu, n_out);
@@ -89,15 +106,16 @@ __global__ void k_move_markers(Geo g, const uint8_t* __restrict__ media,
 }
 
 // cells of the current marker locations (no motion): used after spl_set_markers
+// (count = 0: cells only -- the slabs' pass after the all-reduce of the locations)
 __global__ void k_marker_cells(Geo g, const double* __restrict__ loc, long long n, int h,
                                int ox, int oy, int oz, long long* __restrict__ cell,
-                               MarkerStats* st) {
+                               MarkerStats* st, int count) {
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n;
        m += (long long)gridDim.x * blockDim.x) {
     const double l[3] = {loc[3 * m], loc[3 * m + 1], loc[3 * m + 2]};
     const long long idx = marker_cell(g, l, h, ox, oy, oz);
     cell[m] = idx;
-    if (idx < 0) atomicAdd(&st->outside, 1ull);
+    if (count && idx == MC_OUTSIDE) atomicAdd(&st->outside, 1ull);
   }
 }
 
@@ -158,7 +176,7 @@ __global__ void k_relabel_init(Geo g, WorldBox wb, uint8_t* __restrict__ media,
     const int k = (int)(t / g.ny);
     const uint8_t m0 = media[idx];
     const bool has = mark[idx] != 0;
-    const bool inw = in_world(wb, i, j, k);
+    const bool inw = in_world(wb, i, j, k + g.z0);
     if (has && !inw) atomicAdd(&st->escaped, 1ull);
     const bool fluid = has && inw && m0 != SOLID;
     const uint8_t lab = fluid ? FLUID : (m0 == FLUID ? AIR : m0);
@@ -187,7 +205,8 @@ __global__ void k_relabel_step(Geo g, WorldBox wb, uint8_t* __restrict__ media,
     const int k = (int)(t / g.ny);
     const uint8_t want = (uint8_t)(step - 1);
     const long long off[6] = {-1, 1, -(long long)g.nx, (long long)g.nx, -g.plane, g.plane};
-    const bool inb[6] = {i > 0, i < g.nx - 1, j > 0, j < g.ny - 1, k > 0, k < g.nz - 1};
+    const int kg = k + g.z0;                     // planes -1 / nz of a slab: the z halo
+    const bool inb[6] = {i > 0, i < g.nx - 1, j > 0, j < g.ny - 1, kg > 0, kg < g.nzg - 1};
     bool near = false;
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
@@ -201,7 +220,7 @@ __global__ void k_relabel_step(Geo g, WorldBox wb, uint8_t* __restrict__ media,
       }
     }
     if (near) {
-      if (m0 == ABSENT) media[idx] = in_world(wb, i, j, k) ? AIR : SOLID;
+      if (m0 == ABSENT) media[idx] = in_world(wb, i, j, kg) ? AIR : SOLID;
       layer[idx] = (uint8_t)step;
     }
   }
@@ -242,7 +261,8 @@ __global__ void k_check_surroundings(Geo g, const uint8_t* __restrict__ media,
     const int j = (int)(t % g.ny);
     const int k = (int)(t / g.ny);
     const long long off[6] = {-1, 1, -(long long)g.nx, (long long)g.nx, -g.plane, g.plane};
-    const bool inb[6] = {i > 0, i < g.nx - 1, j > 0, j < g.ny - 1, k > 0, k < g.nz - 1};
+    const int kg = k + g.z0;
+    const bool inb[6] = {i > 0, i < g.nx - 1, j > 0, j < g.ny - 1, kg > 0, kg < g.nzg - 1};
     bool ok = true;
 #pragma unroll
     for (int d = 0; d < 6; ++d) ok &= inb[d] && media[idx + off[d]] != ABSENT;

@@ -98,6 +98,92 @@ def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=
     return res
 
 
+def gather_slabs(arr, plan, world, rank, ny, nx):
+    t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+    if rank != 0:
+        dist.send(t, dst=0)
+        return None
+    bufs = [torch.empty((plan.nz(r), ny, nx), dtype=t.dtype, device="cuda") for r in range(world)]
+    bufs[0].copy_(t)
+    for r in range(1, world):
+        dist.recv(bufs[r], src=r)
+    return torch.cat(bufs, 0).cpu().numpy()
+
+
+def run_markers(world, rank, local, nid, dtype):
+    """Marker stage on slabs (spl_set_markers / spl_move_markers / spl_relabel, then two whole
+    spl_advance steps): every rank holds all markers; labels, fields and marker locations
+    against the same box on one GPU (bit for bit) and against the oracle's relabelling."""
+    H, DT = 10, 0.016671
+    rng = np.random.default_rng(4)
+    n, nzg = 28, 14 * world
+    lab = np.full((nzg, n, n), dr.ABSENT, dtype=np.uint8)
+    lab[6:nzg - 6, 6:22, 6:22] = dr.AIR
+    lab[6:nzg - 6, 6:8, 6:22] = dr.SOLID
+    cells = np.stack([rng.integers(8, 20, 80 * world), rng.integers(8, 20, 80 * world),
+                      rng.integers(8, nzg - 8, 80 * world)], 1)
+    lab[cells[:, 2], cells[:, 1], cells[:, 0]] = dr.FLUID
+    ex = lab != dr.ABSENT
+    U, V, W = (np.where(ex, rng.uniform(-600, 600, lab.shape), 0).astype(dtype) for _ in range(3))
+    P = np.where(lab == dr.FLUID, rng.uniform(0, 1e4, lab.shape), 0).astype(dtype)
+    org = (-14, -14, -14)
+    loc = (cells + np.array(org)) * float(H) + rng.uniform(-4.9, 4.9, cells.shape)
+    lo, hi = (6, 6, 6), (20, 25, nzg - 8)
+    plan = SlabPlan(nzg, world)
+    z0, nz = plan.z0(rank), plan.nz(rank)
+    sl = slice(z0, z0 + nz)
+
+    def stage(s, steps):
+        s.set_world(lo, hi)
+        s.set_markers(loc)
+        moved = s.move_markers(DT)
+        s.relabel(sanity=False)
+        out = [(moved, s.get_markers(), s.download_media(), s.download())]
+        for _ in range(steps):
+            s.advance(DT, sanity=False)
+            out.append((0, s.get_markers(), s.download_media(), s.download()))
+        return out
+
+    with Solver(n, n, nz, dtype=dtype, tol=1e-6, device=local, rank=rank, world=world,
+                nz_global=nzg, z0=z0, nccl_id=nid, origin=org) as s:
+        s.upload(lab[sl], U[sl], V[sl], W[sl], P[sl])
+        mine = stage(s, 2)
+    got = []
+    for moved, mk, med, f in mine:
+        g = {"moved": moved, "markers": mk, "media": gather_slabs(med, plan, world, rank, n, n)}
+        for k in "UVWP":
+            g[k] = gather_slabs(f[k], plan, world, rank, n, n)
+        got.append(g)
+    if rank != 0:
+        return None
+    with Solver(n, n, nzg, dtype=dtype, tol=1e-6, device=local, origin=org) as s1:
+        s1.upload(lab, U, V, W, P)
+        one = stage(s1, 2)
+    new_loc, old, new = dr.move_markers(lab, U, V, W, loc, DT, H, org)
+    want = dr.relabel(lab, U, V, W, P.astype(np.float64), new, lo, hi)
+    ok = True
+    worst = 0.0
+    vs = float(max(np.abs(one[0][3][k]).max() for k in "UVW"))
+    for step, (g, (moved, mk, med, f)) in enumerate(zip(got, one)):
+        ok = ok and np.array_equal(g["media"], med)
+        err = max(float(np.abs(g[k] - f[k]).max()) for k in "UVW") / vs
+        worst = max(worst, err)
+        if step == 0:     # marker motion + relabelling: no reduction involved, bit for bit
+            ok = ok and np.array_equal(g["markers"], mk) and err == 0.0
+            ok = ok and np.array_equal(g["P"], f["P"])
+        else:             # whole advance steps: the fp64 dot products sum in another order
+            ok = ok and err <= 1e-8 and float(np.abs(g["markers"] - mk).max()) <= 1e-6
+    ok = ok and got[0]["moved"] == one[0][0] == int((old != new).any(1).sum())
+    ok = ok and np.array_equal(got[0]["media"], want[0]) and np.array_equal(got[0]["markers"], new_loc)
+    crossed = int((new[:, 2] // 14 != old[:, 2] // 14).sum())
+    return {"case": "markers_on_slabs", "precond": "jacobi", "ok": bool(ok), "world": world,
+            "moved": got[0]["moved"], "markers_that_changed_slab": crossed,
+            "field_err_vs_one_gpu": worst, "fluid_cells": int((got[-1]["media"] == dr.FLUID).sum()),
+            "iters_slab": None, "iters_one_gpu": None, "iters_oracle": None,
+            "vel_err_vs_one_gpu": worst, "vel_err_vs_oracle": 0.0, "p_err_vs_one_gpu": 0.0,
+            "max_abs_div": 0.0, "uneven": False}
+
+
 def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -126,6 +212,13 @@ def main():
         dist.broadcast_object_list(box, src=0)
         r = run_case(name, nx, ny, nzg, dtype, world, rank, local, box[0], fixed, uneven,
                      precond)
+        if rank == 0:
+            results.append(r)
+        dist.barrier()
+    if not only or only in "markers_on_slabs":
+        box = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        r = run_markers(world, rank, local, box[0], np.float64)
         if rank == 0:
             results.append(r)
         dist.barrier()
