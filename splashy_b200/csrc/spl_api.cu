@@ -349,6 +349,7 @@ struct spl_ctx {
   bool mg_no_tma = false;      // SPL_MG_TMA=0: multigrid passes with per-thread cp.async (k_mg_march)
   int mgt_attr_set = 0;
   bool no_ws = false;          // SPL_NO_WS=1: ring kernel without the halo warp (k_phaseA_ring)
+  bool mg_no_fuse_slabs = false;   // SPL_MG_NO_FUSE_SLABS=1: k_phaseB instead of the fused update on slabs
   bool no_quad = false;        // SPL_NO_QUAD=1: one-cell-per-thread div / grad / check kernels
   bool no_gc_fuse = false;     // SPL_NO_GC_FUSE=1: k_grad_sub4 + k_check4 instead of k_grad_check4
   // cell-centred scalar fields advected with the velocity (spl_set_scalars); scal2 = target
@@ -1073,7 +1074,9 @@ struct Impl {
       if (mg_fast(c, v) && ((l == L - 1) ? k >= 2 : nu >= 2)) k -= 1;   // FIRST2 = 2 sweeps
       nxt[l] = (k & 1) ? v.u : v.tmp;
     }
-    xch(0, c->mg[0].b);   // r
+    xch(0, c->mg[0].b);   // r (with fuse_r: the OLD r, combined with q on the fly)
+    if (fuse_r && c->d.world > 1 && xrc == SPL_OK)   // ... and q's boundary planes next to it
+      xrc = exchange_level(c, c->mg[0].g, c->q, sizeof(T), nccl_real(c));
     // levels [lb, L) fit one CTA's shared memory: a single launch runs their sub-cycle
     int lb = L;
     if (L >= 2 && !c->mg_no_bottom)
@@ -1189,10 +1192,13 @@ struct Impl {
   }
 
   // the residual update can ride on the V-cycle's first pass when that pass is the fused
-  // marching kernel on level 0 (fp32, one GPU, at least two levels and two sweeps)
+  // marching kernel on level 0 (fp32, at least two levels and two sweeps).  On z-slabs the pass
+  // forms r' = r - alpha q for the neighbours' boundary planes too, from the halos of r and q:
+  // one more plane exchange (q) instead of a whole k_phaseB pass (SPL_MG_NO_FUSE_SLABS=1: off).
   static bool mg_fuse_ok(const spl_ctx* c) {
     return c->d.precond == SPL_PC_MG && std::is_same<T, float>::value && !c->mg_no_fuse &&
-           c->d.world == 1 && c->mg.size() >= 2 && c->mg_nu >= 2 && mg_fast(c, c->mg[0]) &&
+           (c->d.world == 1 || !c->mg_no_fuse_slabs) && c->mg.size() >= 2 && c->mg_nu >= 2 &&
+           mg_fast(c, c->mg[0]) &&
            c->profile_iters == 0;
   }
   static int precondition(spl_ctx* c, int par, bool fuse_r = false) {
@@ -1948,6 +1954,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
     if (const char* e = getenv("SPL_MG_SUMFORM")) c->mg_sumform = atoi(e) != 0;
     if (const char* e = getenv("SPL_MG_NO_BOTTOM")) c->mg_no_bottom = atoi(e) != 0;
     if (const char* e = getenv("SPL_MG_NO_FUSE")) c->mg_no_fuse = atoi(e) != 0;
+    if (const char* e = getenv("SPL_MG_NO_FUSE_SLABS")) c->mg_no_fuse_slabs = atoi(e) != 0;
     if (c->mg_nu > MG_MAX_NU) c->mg_nu = MG_MAX_NU;
     // Chebyshev weights for the eigenvalues of D^-1 A in [1/3, 2] (the high-frequency
     // band of the 7-point operator under 2x coarsening), ascending; the post-smoother
