@@ -621,8 +621,9 @@ def run_cuda(args):
                        "step": "advect + rhs + PCG + gradient + check",
                        "pcg_iters": args.pcg_iters, "precond": args.precond,
                        "l2": "inputs (3 x 512 MiB fields per GPU) exceed the 126 MB L2; no flush",
-                       "parallelism": f"z-slab x{world}; PCG iteration over peer memory (NVLink "
-                                      f"stores of halo planes and CG scalars), NCCL for the rest"},
+                       "parallelism": ("one GPU, one box" if world == 1 else
+                                       f"z-slab x{world}; PCG iteration over peer memory (NVLink "
+                                       f"stores of halo planes and CG scalars), NCCL for the rest")},
             "pcg_iters_per_s": iters_per_s,
             "stage_ms": stage,
             "wall_ms_per_step": main["wall_ms_per_step"],
