@@ -306,7 +306,8 @@ def timed_steps(D, s, dt, warmup, steps, sampler=None):
 def mgpu_parity(D, iters=40):
     """Slab decomposition against the same box on ONE GPU (both through the C ABI): a
     128 x 64 x 48N vortex, `iters` fixed Jacobi-PCG iterations -- enough z-chunks per slab for
-    the peer-memory iteration, and two x flushes.  The slab result must be bit-identical."""
+    the peer-memory iteration, and two x flushes.  The slab result must equal the one-GPU result
+    to fp32 round-off (`bit_identical` says whether every bit agreed)."""
     import torch
     from splashy_b200 import Solver, scenes
     world, rank = D.world, D.rank
@@ -335,7 +336,10 @@ def mgpu_parity(D, iters=40):
         vs = max(float(np.abs(one[k]).max()) for k in "UVW")
         verr = max(float(np.abs(slab[i] - one[k]).max()) for i, k in enumerate("UVW")) / vs
         perr = float(np.abs(slab[3] - one["P"]).max() / max(1e-30, np.abs(one["P"]).max()))
-        res = {"ok": bool(verr == 0.0 and perr == 0.0), "vel_err": verr, "p_err": perr,
+        # the rank partials of the fp64 dot products are summed in another association than one
+        # GPU's CTA partials, so alpha / beta agree to ~1e-16 and a face whose new value nearly
+        # cancels can round the other way: equal to fp32 round-off, bit-identical in most runs
+        res = {"ok": bool(verr <= 1e-6 and perr <= 1e-6), "vel_err": verr, "p_err": perr,
                "case": f"vortex {nx}x{ny}x{nzg} over {world} slabs vs one GPU, {iters} fixed "
                        f"Jacobi-PCG iterations, fp32", "bit_identical": bool(verr == 0.0 and perr == 0.0)}
     D.barrier()
