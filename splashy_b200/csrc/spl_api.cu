@@ -351,6 +351,7 @@ struct spl_ctx {
   bool no_ws = false;          // SPL_NO_WS=1: ring kernel without the halo warp (k_phaseA_ring)
   bool mg_no_fuse_slabs = false;   // SPL_MG_NO_FUSE_SLABS=1: k_phaseB instead of the fused update on slabs
   bool no_quad = false;        // SPL_NO_QUAD=1: one-cell-per-thread div / grad / check kernels
+  bool no_rb_march = false;    // SPL_NO_RB_MARCH=1: k_rb_black4 / k_rb_red4 instead of k_rb_march
   bool no_gc_fuse = false;     // SPL_NO_GC_FUSE=1: k_grad_sub4 + k_check4 instead of k_grad_check4
   // cell-centred scalar fields advected with the velocity (spl_set_scalars); scal2 = target
   std::vector<char*> scal;
@@ -1205,6 +1206,17 @@ struct Impl {
     if (c->d.precond == SPL_PC_MG) return vcycle(c, par, fuse_r);
     const Geo& g = c->g;
     if constexpr (std::is_same<T, float>::value) {
+      if (g.nx % 4 == 0 && !c->no_quad && !c->no_rb_march) {   // z-marching tiles, each array once
+        const int tx = (g.nx + 127) / 128, ty = (g.ny + RBM_TY - 1) / RBM_TY;
+        const int zc = phaseA_zchunk(c, tx * ty);
+        const dim3 grid(tx, ty, (g.nz + zc - 1) / zc), block(32, RBM_TY);
+        k_rb_march<0><<<grid, block, 0, c->stream>>>(g, c->codes, P(c->r), P(c->einv), P(c->z),
+                                                    c->sc, c->partials, par, zc);
+        k_rb_march<1><<<grid, block, 0, c->stream>>>(g, c->codes, P(c->r), P(c->einv), P(c->z),
+                                                    c->sc, c->partials, par, zc);
+        c->launches += 2;
+        return SPL_OK;
+      }
       if (g.nx % 4 == 0 && !c->no_quad) {     // quad kernels: same z, 30 B / cell
         const int gq = grid_for(c, g.ncell / 4);
         LAUNCH(c, k_rb_black4, gq, 256, g, c->codes, P(c->r), P(c->einv), P(c->z), c->sc);
@@ -1825,6 +1837,7 @@ static int create_impl(spl_ctx* c, const spl_desc* desc) {
   c->tmaps.reserve(256);
   if (const char* e = getenv("SPL_NO_QUAD")) c->no_quad = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_GC_FUSE")) c->no_gc_fuse = atoi(e) != 0;
+  if (const char* e = getenv("SPL_NO_RB_MARCH")) c->no_rb_march = atoi(e) != 0;
   if (const char* e = getenv("SPL_NO_2D_VIEW")) c->no_2d_view = atoi(e) != 0;
   if (const char* e = getenv("SPL_ADV_TMA")) c->adv_tma = atoi(e) != 0;
   if (const char* e = getenv("SPL_ADV_FUSE")) c->adv_fuse = atoi(e) != 0;

@@ -1094,6 +1094,154 @@ k_rb_red4(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ r,
   }
 }
 
+// ---- the two half sweeps as z-marching tile kernels (fp32, nx % 4 = 0) --------------------
+// k_rb_black4 / k_rb_red4 are grid-stride kernels: the quads of the +-z planes, 2 MiB away, are
+// partly read from DRAM a second time (ncu: 1.53 x / 1.18 x the algorithmic bytes).  Here a CTA
+// owns a 128 x 8 tile of the x-y plane and marches along z: the operand of the plane below and
+// the plane itself are carried in registers, the plane above is this iteration's load; the +-y
+// rows and the x neighbours outside the quad come from a double-buffered shared tile written one
+// plane ahead (one barrier per plane, never waiting for a load of its own iteration); only the
+// tile-edge rows / lanes read a halo from global memory.  RED = 0: z_B from r einv of the red
+// neighbours (operands r, einv); RED = 1: z_R from the black z around it, r.z reduced.  Same
+// expressions and neighbour order as k_rb_sweep -> the same z bit for bit.
+constexpr int RBM_TY = 8;
+
+template <int RED>
+__global__ void __launch_bounds__(32 * RBM_TY, 4)
+k_rb_march(Geo g, const uint8_t* __restrict__ codes, const float* __restrict__ r,
+           const float* __restrict__ einv, float* __restrict__ z, Scal* __restrict__ sc,
+           double* __restrict__ partials, int par_slot, int zchunk) {
+  __shared__ float sa[2][RBM_TY + 2][128];               // r (black pass) / z (red pass)
+  __shared__ float se[RED ? 1 : 2][RED ? 1 : RBM_TY + 2][RED ? 4 : 128];   // einv (black pass)
+  __shared__ double red[32];
+  if (sc->done) return;
+  const float* __restrict__ A = RED ? z : r;             // the array whose neighbours are summed
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 128 + 4 * lane, j = blockIdx.y * RBM_TY + ty;
+  const int kb = blockIdx.z * zchunk, ke = min(kb + zchunk, g.nz);
+  const bool act = i < g.nx && j < g.ny;
+  const bool has_xl = act && i > 0, has_xr = act && i + 4 < g.nx;
+  const bool row_lo = (ty == 0), row_hi = (ty == RBM_TY - 1);
+  const bool edge = row_lo || row_hi;
+  const bool edge_in = row_lo ? (i < g.nx && j >= 1 && j - 1 < g.ny) : (i < g.nx && j + 1 < g.ny);
+  const long long eoff = row_lo ? -(long long)g.nx : (long long)g.nx;
+  const int erow = row_lo ? 0 : RBM_TY + 1;
+  const float4 Z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long idx = ((long long)kb * g.ny + j) * g.nx + i;
+  double acc = 0.0;
+
+  float4 am = Z4, ac = Z4, em = Z4, ec = Z4;             // planes k-1 and k of A (and einv)
+  if (act) {
+    ac = ld4(A, idx);
+    if (!RED) ec = ld4(einv, idx);
+    if (kb > 0) {
+      am = ld4(A, idx - g.plane);
+      if (!RED) em = ld4(einv, idx - g.plane);
+    }
+  }
+  *reinterpret_cast<float4*>(&sa[0][ty + 1][4 * lane]) = ac;
+  if (!RED) *reinterpret_cast<float4*>(&se[0][ty + 1][4 * lane]) = ec;
+  if (edge) {
+    *reinterpret_cast<float4*>(&sa[0][erow][4 * lane]) = edge_in ? ld4(A, idx + eoff) : Z4;
+    if (!RED) *reinterpret_cast<float4*>(&se[0][erow][4 * lane]) = edge_in ? ld4(einv, idx + eoff) : Z4;
+  }
+
+  for (int k = kb; k < ke; ++k, idx += g.plane) {
+    const int b = (k - kb) & 1;
+    const bool zm = k > 0, zp = k < g.nz - 1;            // couplings across slabs are dropped
+    // ---- this plane's loads (none is needed before the barrier) -----------------------------
+    unsigned c4 = 0;
+    float4 ap = Z4, ep = Z4, r4 = Z4, e4 = Z4, ha = Z4, he = Z4;
+    float axl = 0.f, axr = 0.f, exl = 0.f, exr = 0.f;
+    if (act) {
+      c4 = *reinterpret_cast<const unsigned*>(codes + idx);
+      if (zp) {
+        ap = ld4(A, idx + g.plane);
+        if (!RED) ep = ld4(einv, idx + g.plane);
+      }
+      if (RED) { r4 = ld4(r, idx); e4 = ld4(einv, idx); }
+      if (lane == 0 && has_xl) { axl = A[idx - 1]; if (!RED) exl = einv[idx - 1]; }
+      if (lane == 31 && has_xr) { axr = A[idx + 4]; if (!RED) exr = einv[idx + 4]; }
+    }
+    if (edge && edge_in && k + 1 < ke) {                 // halo row of plane k+1
+      ha = ld4(A, idx + g.plane + eoff);
+      if (!RED) he = ld4(einv, idx + g.plane + eoff);
+    }
+    __syncthreads();
+    const float4 aym = *reinterpret_cast<const float4*>(&sa[b][ty][4 * lane]);
+    const float4 ayp = *reinterpret_cast<const float4*>(&sa[b][ty + 2][4 * lane]);
+    float4 eym = Z4, eyp = Z4;
+    if (!RED) {
+      eym = *reinterpret_cast<const float4*>(&se[b][ty][4 * lane]);
+      eyp = *reinterpret_cast<const float4*>(&se[b][ty + 2][4 * lane]);
+    }
+    if (lane > 0) { axl = sa[b][ty + 1][4 * lane - 1]; if (!RED) exl = se[b][ty + 1][4 * lane - 1]; }
+    if (lane < 31) { axr = sa[b][ty + 1][4 * lane + 4]; if (!RED) exr = se[b][ty + 1][4 * lane + 4]; }
+    const float ax[6] = {axl, ac.x, ac.y, ac.z, ac.w, axr};      // i-1 .. i+4
+    const float ex[6] = {exl, ec.x, ec.y, ec.z, ec.w, exr};
+    const float ym_[4] = {aym.x, aym.y, aym.z, aym.w}, yp_[4] = {ayp.x, ayp.y, ayp.z, ayp.w};
+    const float eym_[4] = {eym.x, eym.y, eym.z, eym.w}, eyp_[4] = {eyp.x, eyp.y, eyp.z, eyp.w};
+    const float zm_[4] = {am.x, am.y, am.z, am.w}, zp_[4] = {ap.x, ap.y, ap.z, ap.w};
+    const float ezm_[4] = {em.x, em.y, em.z, em.w}, ezp_[4] = {ep.x, ep.y, ep.z, ep.w};
+    const float rr[4] = {RED ? r4.x : ac.x, RED ? r4.y : ac.y, RED ? r4.z : ac.z, RED ? r4.w : ac.w};
+    const float ee[4] = {RED ? e4.x : ec.x, RED ? e4.y : ec.y, RED ? e4.z : ec.z, RED ? e4.w : ec.w};
+    const unsigned p0 = (unsigned)(j + k + g.z0) & 1u;           // colour of cell 0 (1 = black)
+    float zz[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned c = (c4 >> (8 * e)) & 0xffu;
+      const bool black = (((unsigned)e ^ p0) & 1u) != 0u;
+      float v = RED ? ax[e + 1] : 0.f;                   // red pass: black z carried through
+      if (black != (RED != 0)) {                         // the colour this pass computes
+        v = 0.f;
+        if (c & B_FLUID) {
+          float sum = 0.f;
+          if (RED) {
+            if (c & B_XM) sum += ax[e];
+            if (c & B_XP) sum += ax[e + 2];
+            if (c & B_YM) sum += ym_[e];
+            if (c & B_YP) sum += yp_[e];
+            if ((c & B_ZM) && zm) sum += zm_[e];
+            if ((c & B_ZP) && zp) sum += zp_[e];
+          } else {
+            if (c & B_XM) sum = fmaf(ax[e], ex[e], sum);
+            if (c & B_XP) sum = fmaf(ax[e + 2], ex[e + 2], sum);
+            if (c & B_YM) sum = fmaf(ym_[e], eym_[e], sum);
+            if (c & B_YP) sum = fmaf(yp_[e], eyp_[e], sum);
+            if ((c & B_ZM) && zm) sum = fmaf(zm_[e], ezm_[e], sum);
+            if ((c & B_ZP) && zp) sum = fmaf(zp_[e], ezp_[e], sum);
+          }
+          v = (rr[e] + sum) * ee[e];
+        }
+      }
+      zz[e] = v;
+      if (RED) acc += (double)rr[e] * (double)v;
+    }
+    if (act) *reinterpret_cast<float4*>(z + idx) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+    am = ac; ac = ap;
+    if (!RED) { em = ec; ec = ep; }
+    // the next plane's tile rows (read after the next barrier)
+    *reinterpret_cast<float4*>(&sa[b ^ 1][ty + 1][4 * lane]) = ap;
+    if (!RED) *reinterpret_cast<float4*>(&se[b ^ 1][ty + 1][4 * lane]) = ep;
+    if (edge) {
+      *reinterpret_cast<float4*>(&sa[b ^ 1][erow][4 * lane]) = ha;
+      if (!RED) *reinterpret_cast<float4*>(&se[b ^ 1][erow][4 * lane]) = he;
+    }
+  }
+  if (RED) {
+    const double bs = block_sum(acc, red);
+    const unsigned nb = num_blocks();
+    const unsigned tid = lane + 32 * ty;
+    if (tid == 0) partials[linear_block()] = bs;
+    if (last_block(&sc->ticketC, nb)) {
+      double t = 0.0;
+      for (unsigned q = tid; q < nb; q += 32 * RBM_TY) t += __ldcg(partials + q);
+      t = block_sum(t, red);
+      if (tid == 0) sc->gBM[par_slot][sc->rank][0] = t;
+    }
+  }
+}
+
 // ---- deferred pressure update ----------------------------------------------------
 // Iteration it leaves its search direction in ring buffer it % m and its step
 // length in alpha_hist[it % m]; this kernel adds every pending term

@@ -802,29 +802,39 @@ def test_quad_kernels_equal_the_one_cell_kernels_bit_for_bit(shape, monkeypatch)
     assert np.abs(d1 - want)[fl].max() <= 1e-6 * vscale(U, V, W) and np.all(d1[~fl] == 0)
 
 
-@pytest.mark.parametrize("shape", [(64, 48, 24), (8, 5, 3), (132, 9, 2), (36, 20, 12)])
+@pytest.mark.parametrize("shape", [(64, 48, 24), (8, 5, 3), (132, 9, 2), (36, 20, 12), (260, 37, 21)])
 def test_rbic0_quad_sweeps_equal_the_one_cell_sweeps(shape, monkeypatch):
-    """k_rb_black4 / k_rb_red4 (fp32, nx % 4 = 0) against k_rb_sweep on random labels: z = M^-1 r
-    is bit for bit the same, so after K fixed iterations the two solves differ only through the
-    summation order of r.z (<= 1e-5 relative on p, u, v, w); and the quad path converges in the
-    oracle's iteration count (fp64 numpy apply_rbic0) to the direct solve."""
+    """k_rb_march<black|red> (z-marching tiles, the default) and k_rb_black4 / k_rb_red4 (fp32,
+    nx % 4 = 0) against k_rb_sweep on random labels: z = M^-1 r is bit for bit the same, so after
+    K fixed iterations the solves differ only through the summation order of r.z (<= 1e-5
+    relative on p, u, v, w); and the default path converges in the oracle's iteration count
+    (fp64 numpy apply_rbic0) to the direct solve."""
     nx, ny, nz = shape
     sc = scenes.random_box(nx, ny, nz, seed=21, dtype=np.float32, p_solid=0.15, p_air=0.3)
     lab = open_pockets(sc["labels"])
     _, U, V, W = fields(sc, np.float32)
-    res = {}
-    for quad in ("0", "1"):
-        monkeypatch.setenv("SPL_NO_QUAD", "0" if quad == "1" else "1")
+    res, zs = {}, {}
+    rvec = np.where(lab == dr.FLUID, np.random.default_rng(5).uniform(-1, 1, lab.shape), 0
+                    ).astype(np.float32)
+    for mode, env in (("0", {"SPL_NO_QUAD": "1", "SPL_NO_RB_MARCH": "0"}),
+                      ("q", {"SPL_NO_QUAD": "0", "SPL_NO_RB_MARCH": "1"}),
+                      ("m", {"SPL_NO_QUAD": "0", "SPL_NO_RB_MARCH": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         with solver_for(sc, dtype=np.float32, tol=1e-6, max_iters=2000, precond="rbic0") as s:
             s.upload(lab, U, V, W)
+            zs[mode] = s.apply_preconditioner(rvec)[0]          # one application z = M^-1 r
             s.set_fixed_iters(6)
             info = s.project(sc["dt"])
-            res[quad] = (s.download(), info)
-    (g0, i0), (g1, i1) = res["0"], res["1"]
-    assert i0["iters"] == i1["iters"] == 6
-    assert abs(i0["r_inf"] - i1["r_inf"]) <= 1e-4 * i0["b_inf"]
-    for n in "UVWP":
-        assert np.abs(g0[n] - g1[n]).max() <= 1e-5 * vscale(g0[n]), n
+            res[mode] = (s.download(), info)
+    g0, i0 = res["0"]
+    for mode in ("q", "m"):
+        assert np.array_equal(zs[mode], zs["0"]), mode           # bit for bit
+        g1, i1 = res[mode]
+        assert i0["iters"] == i1["iters"] == 6, mode
+        assert abs(i0["r_inf"] - i1["r_inf"]) <= 1e-4 * i0["b_inf"], mode
+        for n in "UVWP":
+            assert np.abs(g0[n] - g1[n]).max() <= 1e-5 * vscale(g0[n]), (mode, n)
     monkeypatch.setenv("SPL_NO_QUAD", "0")
     f64 = [a.astype(np.float64) for a in (U, V, W)]
     with solver_for(sc, dtype=np.float32, tol=1e-6, max_iters=2000, precond="rbic0") as s:
