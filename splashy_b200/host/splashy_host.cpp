@@ -6,8 +6,10 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <memory>
+#include <tuple>
 
 #include "../../include/splashy_cuda.h"
 
@@ -153,6 +155,171 @@ Box pack(const Grid& g) {
     b.p[idx] = c.pressure.value_or(0.0);
   }
   return b;
+}
+
+Grid unpack(const Box& b) {
+  Grid g;
+  std::vector<std::pair<Coord, Cell>> cells;
+  const int h = Constants::h_int;
+  for (int k = 0; k < b.nz; ++k)
+    for (int j = 0; j < b.ny; ++j)
+      for (int i = 0; i < b.nx; ++i) {
+        const size_t idx = ((size_t)k * b.ny + j) * b.nx + i;
+        if (b.media[idx] == SPL_ABSENT) continue;
+        Cell c;
+        c.media = (Media)b.media[idx];
+        c.velocity = Vector3d(b.u[idx], b.v[idx], b.w[idx]);
+        if (c.media != Media::Solid) c.pressure = b.p[idx];
+        cells.push_back({Coord{(i + b.ox) * h, (j + b.oy) * h, (k + b.oz) * h}, c});
+      }
+  g.add_cells(cells);
+  return g;
+}
+
+// ---- state files ------------------------------------------------------------------------
+namespace {
+constexpr char kMagic[8] = {'S', 'P', 'L', 'S', 'T', 'A', 'T', 'E'};
+struct File {
+  FILE* f;
+  std::string path;
+  File(const std::string& p, const char* mode) : f(std::fopen(p.c_str(), mode)), path(p) {
+    if (!f) throw Failure("cannot open state file " + p);
+  }
+  ~File() { if (f) std::fclose(f); }
+  void put(const void* d, size_t n) {
+    if (n && std::fwrite(d, 1, n, f) != n) throw Failure("short write to " + path);
+  }
+  void get(void* d, size_t n) {
+    if (n && std::fread(d, 1, n, f) != n) throw Failure("state file " + path + " is truncated");
+  }
+  template <typename V> void put(const V& v) { put(&v, sizeof v); }
+  template <typename V> V get() { V v; get(&v, sizeof v); return v; }
+};
+void put_header(File& f, uint32_t kind) {
+  f.put(kMagic, 8);
+  f.put<uint32_t>(1);
+  f.put<uint32_t>(kind);
+}
+void get_header(File& f, uint32_t kind) {
+  char m[8];
+  f.get(m, 8);
+  if (std::memcmp(m, kMagic, 8) != 0) throw Failure(f.path + " is not a SPLSTATE file");
+  const uint32_t version = f.get<uint32_t>(), k = f.get<uint32_t>();
+  if (version != 1) throw Failure(f.path + ": unsupported SPLSTATE version");
+  if (k != kind) throw Failure(f.path + (kind ? ": not a dense box" : ": not a sparse grid"));
+}
+}  // namespace
+
+void save_grid(const std::string& path, const Grid& g) {
+  std::vector<std::pair<Coord, Cell>> cells(g.cells().begin(), g.cells().end());
+  std::sort(cells.begin(), cells.end(), [](const auto& a, const auto& b) {
+    return std::tie(a.first.z, a.first.y, a.first.x) < std::tie(b.first.z, b.first.y, b.first.x);
+  });
+  File f(path, "wb");
+  put_header(f, 0);
+  f.put<double>(Constants::h);
+  f.put<uint64_t>(cells.size());
+  for (const auto& kv : cells) {
+    const int32_t xyz[3] = {kv.first.x, kv.first.y, kv.first.z};
+    const uint8_t tag[4] = {(uint8_t)kv.second.media, (uint8_t)(kv.second.pressure ? 1 : 0), 0, 0};
+    const double val[4] = {kv.second.velocity.x, kv.second.velocity.y, kv.second.velocity.z,
+                           kv.second.pressure.value_or(0.0)};
+    f.put(xyz, sizeof xyz);
+    f.put(tag, sizeof tag);
+    f.put(val, sizeof val);
+  }
+}
+
+Grid load_grid(const std::string& path) {
+  File f(path, "rb");
+  get_header(f, 0);
+  const double h = f.get<double>();
+  if (h != Constants::h) throw Failure(path + ": cell size differs from Constants.h");
+  const uint64_t n = f.get<uint64_t>();
+  std::vector<std::pair<Coord, Cell>> cells;
+  cells.reserve(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    int32_t xyz[3];
+    uint8_t tag[4];
+    double val[4];
+    f.get(xyz, sizeof xyz);
+    f.get(tag, sizeof tag);
+    f.get(val, sizeof val);
+    if (tag[0] > 2) throw Failure(path + ": unknown media value");
+    Cell c;
+    c.media = (Media)tag[0];
+    c.velocity = Vector3d(val[0], val[1], val[2]);     // refuses NaN / Inf like Vector.fs:15-18
+    if (tag[1]) c.pressure = val[3];
+    cells.push_back({Coord{xyz[0], xyz[1], xyz[2]}, c});
+  }
+  Grid g;
+  g.add_cells(cells);
+  return g;
+}
+
+void save_box(const std::string& path, const Box& b) {
+  File f(path, "wb");
+  put_header(f, 1);
+  const int32_t dims[6] = {b.nx, b.ny, b.nz, b.ox, b.oy, b.oz};
+  f.put(dims, sizeof dims);
+  f.put<double>(Constants::h);
+  const size_t n = (size_t)b.nx * b.ny * b.nz;
+  f.put(b.media.data(), n);
+  for (const std::vector<double>* a : {&b.u, &b.v, &b.w, &b.p}) f.put(a->data(), n * sizeof(double));
+}
+
+Box load_box(const std::string& path) {
+  File f(path, "rb");
+  get_header(f, 1);
+  int32_t dims[6];
+  f.get(dims, sizeof dims);
+  const double h = f.get<double>();
+  if (h != Constants::h) throw Failure(path + ": cell size differs from Constants.h");
+  if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) throw Failure(path + ": empty box");
+  Box b;
+  b.nx = dims[0]; b.ny = dims[1]; b.nz = dims[2];
+  b.ox = dims[3]; b.oy = dims[4]; b.oz = dims[5];
+  const size_t n = (size_t)b.nx * b.ny * b.nz;
+  b.media.resize(n);
+  f.get(b.media.data(), n);
+  for (std::vector<double>* a : {&b.u, &b.v, &b.w, &b.p}) {
+    a->resize(n);
+    f.get(a->data(), n * sizeof(double));
+  }
+  return b;
+}
+
+namespace {
+// NumPy format 1.0: magic, version, u16 header length, ASCII dict padded to a multiple of 64
+void write_npy(const std::string& path, const char* descr, const Box& b, const void* data,
+               size_t bytes) {
+  std::string hd = std::string("{'descr': '") + descr + "', 'fortran_order': False, 'shape': (" +
+                   std::to_string(b.nz) + ", " + std::to_string(b.ny) + ", " +
+                   std::to_string(b.nx) + "), }";
+  while ((10 + hd.size() + 1) % 64 != 0) hd += ' ';
+  hd += '\n';
+  File f(path, "wb");
+  const unsigned char pre[8] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0};
+  f.put(pre, 8);
+  f.put<uint16_t>((uint16_t)hd.size());
+  f.put(hd.data(), hd.size());
+  f.put(data, bytes);
+}
+}  // namespace
+
+void save_box_npy(const std::string& dir, const Box& b) {
+  const size_t n = (size_t)b.nx * b.ny * b.nz;
+  write_npy(dir + "/media.npy", "|u1", b, b.media.data(), n);
+  write_npy(dir + "/u.npy", "<f8", b, b.u.data(), n * sizeof(double));
+  write_npy(dir + "/v.npy", "<f8", b, b.v.data(), n * sizeof(double));
+  write_npy(dir + "/w.npy", "<f8", b, b.w.data(), n * sizeof(double));
+  write_npy(dir + "/p.npy", "<f8", b, b.p.data(), n * sizeof(double));
+  File f(dir + "/meta.json", "wb");
+  const std::string meta = "{\"origin\": [" + std::to_string(b.ox) + ", " + std::to_string(b.oy) + ", " +
+                           std::to_string(b.oz) + "], \"h\": " + std::to_string(Constants::h_int) +
+                           ", \"shape\": [" + std::to_string(b.nz) + ", " + std::to_string(b.ny) +
+                           ", " + std::to_string(b.nx) + "]}\n";
+  f.put(meta.data(), meta.size());
 }
 
 // ---- Solver ---------------------------------------------------------------------------
@@ -393,22 +560,7 @@ Grid Simulator::snapshot() {
   if (!uploaded_) return grid_;
   fail_if(spl_download(ctx_, box_.u.data(), box_.v.data(), box_.w.data(), box_.p.data(), nullptr));
   fail_if(spl_download_media(ctx_, box_.media.data()));
-  Grid g;
-  std::vector<std::pair<Coord, Cell>> cells;
-  const int h = Constants::h_int;
-  for (int k = 0; k < box_.nz; ++k)
-    for (int j = 0; j < box_.ny; ++j)
-      for (int i = 0; i < box_.nx; ++i) {
-        const size_t idx = ((size_t)k * box_.ny + j) * box_.nx + i;
-        if (box_.media[idx] == SPL_ABSENT) continue;
-        Cell c;
-        c.media = (Media)box_.media[idx];
-        c.velocity = Vector3d(box_.u[idx], box_.v[idx], box_.w[idx]);
-        if (c.media != Media::Solid) c.pressure = box_.p[idx];
-        cells.push_back({Coord{(i + box_.ox) * h, (j + box_.oy) * h, (k + box_.oz) * h}, c});
-      }
-  g.add_cells(cells);
-  return g;
+  return unpack(box_);
 }
 
 }  // namespace splashy
@@ -478,6 +630,20 @@ int splh_get_cell(void* hp, int x, int y, int z, int* media, double* vel, int* h
   });
 }
 int splh_size(void* hp) { return (int)static_cast<Host*>(hp)->grid.size(); }
+// state files (splashy_host.hpp): kind 0 = sparse grid, 1 = dense box, 2 = NumPy directory
+int splh_save(void* hp, int kind, const char* path) {
+  return guarded([&] {
+    const Grid& g = static_cast<Host*>(hp)->grid;
+    if (kind == 0) save_grid(path, g);
+    else if (kind == 1) save_box(path, pack(g));
+    else save_box_npy(path, pack(g));
+  });
+}
+int splh_load(void* hp, int kind, const char* path) {
+  return guarded([&] {
+    static_cast<Host*>(hp)->grid = (kind == 0) ? load_grid(path) : unpack(load_box(path));
+  });
+}
 int splh_update_velocity(void* hp, int x, int y, int z, double vx, double vy, double vz) {
   return guarded([&] {
     static_cast<Host*>(hp)->grid.update_velocities({{Coord{x, y, z}, Vector3d(vx, vy, vz)}});

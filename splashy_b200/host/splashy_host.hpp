@@ -97,6 +97,24 @@ struct Box {
   long index(const Coord& c) const;      // -1 when outside
 };
 Box pack(const Grid& g);
+Grid unpack(const Box& b);             // absent cells dropped; pressure: Some p on non-Solid cells
+
+// ---- state files: how a Grid / a dense Box leaves and enters the host ------
+// One little-endian container, "SPLSTATE" + u32 version (1) + u32 kind:
+//   kind 0, sparse grid   f64 h, u64 count, then per cell (sorted by z, y, x)
+//                         i32 x, y, z (world coordinates, multiples of h), u8 media,
+//                         u8 has_pressure, 2 pad bytes, f64 vx, vy, vz, pressure      (48 B)
+//   kind 1, dense box     i32 nx, ny, nz, ox, oy, oz (origin in cells), f64 h, then
+//                         u8 media[n] (255 = absent), f64 u[n], v[n], w[n], p[n], x fastest
+// -- what Grid.fs:12's Dictionary<Coord,Cell> is written as by the F# shim of INTEGRATION.md
+// (BinaryWriter) and read by splashy_b200/state_io.py, and the other way round.  save_box_npy
+// writes the dense arrays as standard NumPy files (media.npy u8, u/v/w/p.npy f64, shape
+// (nz, ny, nx)) plus meta.json (origin, h) into a directory.
+void save_grid(const std::string& path, const Grid& g);
+Grid load_grid(const std::string& path);
+void save_box(const std::string& path, const Box& b);
+Box load_box(const std::string& path);
+void save_box_npy(const std::string& dir, const Box& b);
 
 // The solver terms that run on the GPU.  One Solver = one spl_ctx (recreated when
 // the packed box changes shape); fp64 like the reference.

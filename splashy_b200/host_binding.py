@@ -33,6 +33,8 @@ def load():
     lib.splh_get_cell.argtypes = [C.c_void_p] + [C.c_int] * 3 + [C.POINTER(C.c_int), C.POINTER(C.c_double),
                                                               C.POINTER(C.c_int), C.POINTER(C.c_double)]
     lib.splh_size.argtypes = [C.c_void_p]
+    lib.splh_save.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    lib.splh_load.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     lib.splh_update_velocity.argtypes = [C.c_void_p] + [C.c_int] * 3 + [C.c_double] * 3
     lib.splh_update_media.argtypes = [C.c_void_p] + [C.c_int] * 4
     lib.splh_pressure_divergence.argtypes = [C.c_void_p] + [C.c_int] * 3 + [C.POINTER(C.c_double)]
@@ -105,6 +107,14 @@ class Host:
 
     def size(self) -> int:
         return self._lib.splh_size(self._h)
+
+    # state files (splashy_host.hpp save_grid / save_box / save_box_npy, load_grid / load_box)
+    def save(self, path, kind: str = "grid"):
+        self._ok(self._lib.splh_save(self._h, {"grid": 0, "box": 1, "npy": 2}[kind],
+                                     str(path).encode()))
+
+    def load(self, path, kind: str = "grid"):
+        self._ok(self._lib.splh_load(self._h, {"grid": 0, "box": 1}[kind], str(path).encode()))
 
     def update_velocity(self, coord, v):
         self._ok(self._lib.splh_update_velocity(self._h, *coord, *v))
