@@ -83,6 +83,10 @@ def run_case(name, nx, ny, nzg, dtype, world, rank, local, nid, fixed=0, uneven=
               and info["max_abs_div"] <= (1e-4 if dtype == np.float32 else 1e-8) * vs)
         if fixed:
             ok = err_one <= lim and info["iters"] == fixed
+        if precond == "rbic0":
+            ok = (err_orc <= lim and err_one <= lim and info["converged"] == 1
+                  and info["iters"] <= 2 * info1["iters"] + 5
+                  and info["max_abs_div"] <= (1e-4 if dtype == np.float32 else 1e-8) * vs)
         if precond == "mg":
             # the slab hierarchy (levels stop where a rank runs out of planes, the bottom
             # of the cycle is block-local) is a different -- equally valid -- preconditioner
@@ -200,6 +204,10 @@ def main():
              ("vortex_f32_split_fixed", 128, 64, 48 * world, np.float32, 40, False),
              ("vortex_f32_split", 128, 64, 48 * world, np.float32, 0, False)]
     cases = [c + ("jacobi",) for c in cases]
+    # RB-IC(0) on slabs is block-Jacobi over the slabs (couplings across a slab boundary are
+    # dropped): another preconditioner than the one-GPU one, the same converged answer
+    cases += [("rbic0_f32_march", 128, 48, 24 * world, np.float32, 0, False, "rbic0"),
+              ("rbic0_f64", 36, 20, 12 * world, np.float64, 0, False, "rbic0")]
     cases += [("mg_f32_march_bottom", 128, 64, 32 * world, np.float32, 0, False, "mg"),
               ("mg_f64_uneven", 24, 20, 32 + 2 * (world - 1), np.float64, 0, True, "mg"),
               ("mg_f32_small", 64, 48, 16 * world, np.float32, 0, False, "mg"),
